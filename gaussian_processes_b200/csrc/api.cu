@@ -1,0 +1,340 @@
+// api.cu -- extern "C" surface of libgpb200.so (declared in include/gpb200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/gpb200.h"
+#include "kfunctors.cuh"
+#include "launch.h"
+
+long long g_gpb_launches = 0;
+static thread_local char g_err[512] = "";
+
+void gpb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int gpb_check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return GPB_OK;
+    gpb_set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return GPB_ERR_CUDA;
+}
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline long long roundup(long long n, long long m) { return (n + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------
+// eval finalisation: assemble {log_lh, dloglh[...], logdet, quad, info} per candidate
+// ---------------------------------------------------------------------------
+__global__ void eval_finalize_kernel(const double* out3, const double* out8, const int* info,
+                                     const KParams* Pb, int kind, int want_grad, int batch,
+                                     double* result) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int np = kind == GPB_GAUSSIAN ? 2 : 3;
+    double* r = result + (long long)b * 8;
+    const bool bad = info[b] != 0;
+    r[0] = out3[b * 3 + 0];
+    for (int i = 1; i <= 4; i++) r[i] = 0.0;
+    if (want_grad) {
+        const double* q = out8 + (long long)b * 16;
+        const double s = Pb[b].s;
+        for (int i = 0; i < np; i++)      // gp_c.pyx:47-49: 0.5*y^T(Ki dK)Kiy - 0.5*tr(Ki dK)
+            r[1 + i] = bad ? NAN : 0.5 * q[i] + -0.5 * q[6 + i];
+        // noise row: dK = 2 s I  (gp_c.pyx:45)
+        r[1 + np] = bad ? NAN : 0.5 * (2.0 * s * q[13]) + -0.5 * (2.0 * s * q[12]);
+    }
+    r[5] = out3[b * 3 + 1];
+    r[6] = out3[b * 3 + 2];
+    r[7] = (double)info[b];
+}
+
+struct EvalWs {
+    double *L, *W, *V, *Ki, *z, *alpha, *ypad, *partial, *out3, *out8;
+    KParams* Pb;
+    int *info, *flags;
+    size_t bytes;
+};
+
+static EvalWs carve(char* base, long long n, int batch, int want_grad) {
+    const long long np_ = roundup(n, GPB_NB), T = np_ / GPB_NB;
+    const size_t mat = (size_t)batch * np_ * np_ * 8;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t off = 0;
+    EvalWs w;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += al(bytes); return p; };
+    w.L = (double*)take(mat);
+    w.W = (double*)take(mat);
+    w.V = (double*)take(want_grad ? mat : 0);
+    w.Ki = (double*)take(want_grad ? mat : 0);
+    w.z = (double*)take((size_t)batch * np_ * 8);
+    w.alpha = (double*)take((size_t)batch * np_ * 8);
+    w.ypad = (double*)take((size_t)np_ * 8);
+    w.partial = (double*)take((size_t)batch * gpb_grad_reduce_blocks(n) * 16 * 8);
+    w.out3 = (double*)take((size_t)batch * 3 * 8);
+    w.out8 = (double*)take((size_t)batch * 16 * 8);
+    w.Pb = (KParams*)take((size_t)batch * sizeof(KParams));
+    w.info = (int*)take((size_t)batch * 4);
+    w.flags = (int*)take(((size_t)2 * batch * T + 2) * 4);
+    w.bytes = off;
+    return w;
+}
+
+// host-API device memory pool (grow-only)
+static void* g_pool = nullptr;
+static size_t g_pool_bytes = 0;
+static int pool_reserve(size_t bytes) {
+    if (bytes <= g_pool_bytes) return GPB_OK;
+    if (g_pool) GPB_CUDA(cudaFree(g_pool));
+    g_pool = nullptr;
+    g_pool_bytes = 0;
+    GPB_CUDA(cudaMalloc(&g_pool, bytes));
+    g_pool_bytes = bytes;
+    return GPB_OK;
+}
+
+extern "C" {
+
+int gpb_version(void) { return 100; }
+const char* gpb_last_error(void) { return g_err; }
+double gpb_min_log(void) { return GPB_MIN_LOG; }
+int64_t gpb_launch_count(void) { return g_gpb_launches; }
+
+int gpb_kernel_build(int kind, const double* theta, double s, const double* x1, int64_t n1,
+                     const double* x2, int64_t n2, int64_t rows, int64_t cols, unsigned slice_mask,
+                     double* out, int64_t ld, int64_t slice_stride, int add_diag, int pad_identity,
+                     void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(theta && out, "null pointer");
+    KParams P;
+    gpb_make_kparams(&P, kind, theta, s);
+    double* outs[GPB_MAX_SLICES];
+    int q = 0;
+    for (int sidx = 0; sidx < GPB_MAX_SLICES; sidx++) {
+        if (sidx < gpb_n_slices(kind) && (slice_mask >> sidx) & 1u) outs[sidx] = out + (long long)(q++) * slice_stride;
+        else outs[sidx] = nullptr;
+    }
+    return gpb_launch_build(kind, &P, nullptr, 1, x1, n1, x2, n2, rows, cols, outs, ld, 0, add_diag,
+                            pad_identity, S(stream));
+}
+
+int gpb_kernel_matvec(int kind, const double* theta, const double* x1, int64_t n1, const double* x2,
+                      int64_t n2, int npairs, const int* slice, const int* outidx, const double* coef,
+                      const double* const* vec, int nout, double* const* out, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    KParams P;
+    gpb_make_kparams(&P, kind, theta, 0.0);
+    return gpb_launch_fused_matvec(kind, &P, nullptr, 1, x1, n1, x2, n2, npairs, slice, outidx, coef, vec,
+                                   nout, out, 0, 0, S(stream));
+}
+
+int gpb_potrf(double* A, int64_t n, int64_t ld, int64_t stride_a, int batch, double* W, int64_t ldw,
+              int64_t stride_w, double* V, int64_t ldv, int64_t stride_v, int* info, void* stream) {
+    return gpb_launch_potrf(A, n, ld, stride_a, batch, W, ldw, stride_w, V, ldv, stride_v, info, S(stream));
+}
+
+int gpb_potrs(const double* L, const double* W, int64_t n, int64_t ld, int64_t ldw, int64_t stride_l,
+              int64_t stride_w, int batch, const double* y, int64_t stride_y, double* z, double* alpha,
+              int64_t stride_vec, int* flags, void* stream) {
+    return gpb_launch_potrs(L, W, n, ld, ldw, stride_l, stride_w, batch, y, stride_y, z, alpha, stride_vec,
+                            flags, S(stream));
+}
+
+int gpb_trtri(const double* L, int64_t n, int64_t ld, int64_t stride_l, int batch, double* W,
+              int64_t ldw, int64_t stride_w, double* V, int64_t ldv, int64_t stride_v, double* T,
+              int64_t ldt, int64_t stride_t, void* stream) {
+    return gpb_launch_trtri(L, n, ld, stride_l, batch, W, ldw, stride_w, V, ldv, stride_v, T, ldt,
+                            stride_t, S(stream));
+}
+
+int gpb_lauum(const double* V, int64_t n, int64_t ldv, int64_t stride_v, int batch, double* Ki,
+              int64_t ldk, int64_t stride_k, void* stream) {
+    return gpb_launch_lauum(V, n, ldv, stride_v, batch, Ki, ldk, stride_k, S(stream));
+}
+
+int gpb_tril(double* A, int64_t n, int64_t ld, void* stream) {
+    return gpb_launch_tril(A, n, ld, 0, 1, S(stream));
+}
+
+int gpb_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
+               void* stream) {
+    return gpb_launch_copy2d(dst, ldd, src, lds, rows, cols, 0, 0, 1, S(stream));
+}
+
+int gpb_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                double* Ct, int64_t ldct, int64_t M, int64_t N, int64_t K, double alpha, double beta,
+                int a_tri, int b_tri, int lower_only, void* stream) {
+    GpbGemm g = gpb_gemm_default();
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.Ct = Ct; g.ldct = ldct;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K; g.alpha = alpha; g.beta = beta;
+    g.a_tri = a_tri; g.b_tri = b_tri; g.lower_only = lower_only;
+    return gpb_launch_gemm(g, 1, S(stream));
+}
+
+int gpb_loglh(const double* L, int64_t n_valid, int64_t ld, const double* y, const double* alpha,
+              const int* info, double* out3, void* stream) {
+    return gpb_launch_loglh(L, n_valid, ld, 0, 1, y, 0, alpha, 0, info, out3, S(stream));
+}
+
+int64_t gpb_grad_partial_doubles(int64_t n) { return (int64_t)gpb_grad_reduce_blocks(n) * 16; }
+
+int gpb_slice_reduce(int kind, const double* theta, const double* x, int64_t n, const double* Ki,
+                     int64_t ldk, const double* alpha, int nslices, const int* slices,
+                     double* partial, double* out16, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    KParams P;
+    gpb_make_kparams(&P, kind, theta, 0.0);
+    return gpb_launch_grad_reduce(kind, &P, nullptr, 1, x, n, Ki, ldk, 0, alpha, 0, nslices, slices,
+                                  partial, out16, S(stream));
+}
+
+int gpb_gemv(const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y,
+             double alpha, double beta, void* stream) {
+    return gpb_launch_gemv(A, rows, cols, lda, x, y, alpha, beta, S(stream));
+}
+
+int gpb_trace_prod(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t n,
+                   double* partial, double* out, void* stream) {
+    return gpb_launch_trace_prod(A, lda, B, ldb, n, partial, out, S(stream));
+}
+
+int gpb_quadform(const double* u, const double* M, int64_t ldm, const double* v, int64_t n,
+                 double* partial, double* out, void* stream) {
+    return gpb_launch_quadform(u, M, ldm, v, n, partial, out, S(stream));
+}
+
+size_t gpb_eval_workspace_bytes(int64_t n, int batch, int want_grad) {
+    return carve(nullptr, n, batch, want_grad).bytes;
+}
+
+int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, const double* y, int64_t n,
+                int want_grad, void* workspace, size_t workspace_bytes, double* result, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(batch >= 1 && n >= 1 && thetas && x && y && workspace && result, "bad argument");
+    EvalWs w = carve((char*)workspace, n, batch, want_grad);
+    GPB_REQUIRE(w.bytes <= workspace_bytes, "workspace too small (see gpb_eval_workspace_bytes)");
+    GPB_REQUIRE((uintptr_t)workspace % 256 == 0, "workspace must be 256-byte aligned");
+    cudaStream_t st = S(stream);
+    const long long np_ = roundup(n, GPB_NB);
+    const long long mstride = np_ * np_;
+    const int nth = gpb_n_kparams(kind) + 1;
+
+    std::vector<KParams> hp((size_t)batch);
+    for (int b = 0; b < batch; b++) gpb_make_kparams(&hp[b], kind, thetas + (long long)b * nth, thetas[(long long)b * nth + nth - 1]);
+    GPB_CUDA(cudaMemcpyAsync(w.Pb, hp.data(), sizeof(KParams) * batch, cudaMemcpyHostToDevice, st));
+    GPB_CUDA(cudaStreamSynchronize(st));   // hp is a stack-lifetime staging buffer
+    GPB_CUDA(cudaMemsetAsync(w.ypad, 0, np_ * 8, st));
+    GPB_CUDA(cudaMemcpyAsync(w.ypad, y, n * 8, cudaMemcpyDeviceToDevice, st));
+
+    // Kxx + s^2 I straight into the factorisation buffer, identity in the pad
+    double* outs[GPB_MAX_SLICES] = {nullptr};
+    outs[0] = w.L;
+    int stt = gpb_launch_build(kind, nullptr, w.Pb, batch, x, n, x, n, np_, np_, outs, np_, mstride, 1, 1, st);
+    if (stt) return stt;
+    stt = gpb_launch_potrf(w.L, np_, np_, mstride, batch, w.W, np_, mstride, want_grad ? w.V : nullptr, np_, mstride, w.info, st);
+    if (stt) return stt;
+    stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, mstride, mstride, batch, w.ypad, 0, w.z, w.alpha, np_, w.flags, st);
+    if (stt) return stt;
+    stt = gpb_launch_loglh(w.L, n, np_, mstride, batch, w.ypad, 0, w.alpha, np_, w.info, w.out3, st);
+    if (stt) return stt;
+    if (want_grad) {
+        stt = gpb_launch_trtri(w.L, np_, np_, mstride, batch, w.W, np_, mstride, w.V, np_, mstride, w.Ki, np_, mstride, st);
+        if (stt) return stt;
+        stt = gpb_launch_lauum(w.V, np_, np_, mstride, batch, w.Ki, np_, mstride, st);
+        if (stt) return stt;
+        const int jsl[3] = {1, 2, 3};
+        stt = gpb_launch_grad_reduce(kind, nullptr, w.Pb, batch, x, n, w.Ki, np_, mstride, w.alpha, np_,
+                                     gpb_n_kparams(kind), jsl, w.partial, w.out8, st);
+        if (stt) return stt;
+    }
+    eval_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.out3, w.out8, w.info, w.Pb, kind, want_grad, batch, result);
+    GPB_LAUNCH_CHECK("eval_finalize_kernel");
+    return GPB_OK;
+}
+
+int gpb_gp_eval_host(int kind, const double* thetas, int batch, const double* x, const double* y,
+                     int64_t n, int want_grad, double* result) {
+    GPB_REQUIRE(batch >= 1 && n >= 1 && thetas && x && y && result, "bad argument");
+    const size_t wsb = gpb_eval_workspace_bytes(n, batch, want_grad);
+    const size_t extra = (size_t)(2 * n + 8 * (size_t)batch) * 8 + 1024;
+    int stt = pool_reserve(wsb + extra);
+    if (stt) return stt;
+    char* base = (char*)g_pool;
+    double* dx = (double*)(base + wsb);
+    double* dy = dx + n;
+    double* dres = dy + n;
+    GPB_CUDA(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, 0));
+    GPB_CUDA(cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, 0));
+    stt = gpb_gp_eval(kind, thetas, batch, dx, dy, n, want_grad, base, wsb, dres, nullptr);
+    if (stt) return stt;
+    GPB_CUDA(cudaMemcpyAsync(result, dres, (size_t)batch * 8 * 8, cudaMemcpyDeviceToHost, 0));
+    GPB_CUDA(cudaStreamSynchronize(0));
+    return GPB_OK;
+}
+
+// ---- host-buffer drop-ins for the Cython signatures --------------------------------
+int gpb_kernel_slices_host(int kind, unsigned slice_mask, double* out, const double* x1, int64_t n1,
+                           const double* x2, int64_t n2, const double* theta) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(out && x1 && x2 && theta && n1 >= 0 && n2 >= 0, "bad argument");
+    if (n1 == 0 || n2 == 0) return GPB_OK;
+    int ns = 0;
+    for (int s = 0; s < gpb_n_slices(kind); s++) ns += (slice_mask >> s) & 1u;
+    GPB_REQUIRE(ns > 0, "empty slice mask");
+    const size_t xb = (size_t)roundup((n1 + n2) * 8, 256);
+    const size_t ob = (size_t)ns * n1 * n2 * 8;
+    int stt = pool_reserve(xb + ob);
+    if (stt) return stt;
+    double* dx1 = (double*)g_pool;
+    double* dx2 = dx1 + n1;
+    double* dout = (double*)((char*)g_pool + xb);
+    GPB_CUDA(cudaMemcpyAsync(dx1, x1, n1 * 8, cudaMemcpyHostToDevice, 0));
+    GPB_CUDA(cudaMemcpyAsync(dx2, x2, n2 * 8, cudaMemcpyHostToDevice, 0));
+    stt = gpb_kernel_build(kind, theta, 0.0, dx1, n1, dx2, n2, n1, n2, slice_mask, dout, n2, n1 * n2, 0, 0, nullptr);
+    if (stt) return stt;
+    GPB_CUDA(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, 0));
+    GPB_CUDA(cudaStreamSynchronize(0));
+    return GPB_OK;
+}
+
+#define GPB_G(name, mask)                                                                              \
+    int gpb_gaussian_##name(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2,  \
+                            double h, double w) {                                                      \
+        const double th[2] = {h, w};                                                                   \
+        return gpb_kernel_slices_host(GPB_GAUSSIAN, mask, out, x1, n1, x2, n2, th);                    \
+    }
+#define GPB_P(name, mask)                                                                              \
+    int gpb_periodic_##name(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2,  \
+                            double h, double w, double p) {                                            \
+        const double th[3] = {h, w, p};                                                                \
+        return gpb_kernel_slices_host(GPB_PERIODIC, mask, out, x1, n1, x2, n2, th);                    \
+    }
+GPB_G(K, 0x01u)
+GPB_G(jacobian, 0x06u)
+GPB_G(hessian, 0x78u)
+GPB_G(dK_dh, 1u << 1)
+GPB_G(dK_dw, 1u << 2)
+GPB_G(d2K_dhdh, 1u << 3)
+GPB_G(d2K_dhdw, 1u << 4)
+GPB_G(d2K_dwdh, 1u << 5)
+GPB_G(d2K_dwdw, 1u << 6)
+GPB_P(K, 0x0001u)
+GPB_P(jacobian, 0x000Eu)
+GPB_P(hessian, 0x1FF0u)
+GPB_P(dK_dh, 1u << 1)
+GPB_P(dK_dw, 1u << 2)
+GPB_P(dK_dp, 1u << 3)
+GPB_P(d2K_dhdh, 1u << 4)
+GPB_P(d2K_dhdw, 1u << 5)
+GPB_P(d2K_dhdp, 1u << 6)
+GPB_P(d2K_dwdh, 1u << 7)
+GPB_P(d2K_dwdw, 1u << 8)
+GPB_P(d2K_dwdp, 1u << 9)
+GPB_P(d2K_dpdh, 1u << 10)
+GPB_P(d2K_dpdw, 1u << 11)
+GPB_P(d2K_dpdp, 1u << 12)
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+// build.cu -- kernel-matrix builders and the kernels that consume kernel values
+// without materialising them (fused kernel-times-vector products, fused gradient
+// reductions over K^-1).  All fp64, HBM-write-bound (builders) or FP64-ALU-bound
+// (fused consumers).  Replaces gp/ext/gaussian_c.pyx and periodic_c.pyx.
+#include "kfunctors.cuh"
+#include "launch.h"
+
+// ---------------------------------------------------------------------------
+// 1. slice builder: any subset of {K, jacobian slices, hessian slices} in one pass
+// ---------------------------------------------------------------------------
+struct BuildArgs {
+    KParams P;
+    const KParams* Pb;     // per-batch parameters (device) or nullptr -> P
+    const double* x1;
+    const double* x2;
+    long long n1, n2;      // valid extents
+    long long rows, cols;  // extents to fill (>= n1, n2): the pad region gets 0 / identity
+    double* out[GPB_MAX_SLICES];
+    long long ld;
+    long long bstride;     // batch stride of every out[] slice
+    int add_diag;          // slice 0: += s^2 on the index diagonal (gp.py:265)
+    int pad_identity;      // slice 0: 1.0 on the diagonal of the pad region
+};
+
+template <int KIND>
+__device__ __forceinline__ void load_kparams(KParams* sP, const KParams& byval, const KParams* Pb, int b) {
+    if (Pb) {
+        const double* src = reinterpret_cast<const double*>(Pb + b);
+        double* dst = reinterpret_cast<double*>(sP);
+        for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < (int)(sizeof(KParams) / 8);
+             i += blockDim.x * blockDim.y)
+            dst[i] = src[i];
+    } else if (threadIdx.x == 0 && threadIdx.y == 0) {
+        *sP = byval;
+    }
+    __syncthreads();
+}
+
+// block (32, 8): each thread owns 2 adjacent columns and 4 rows (stride 8) of a 32 x 64 tile.
+template <int KIND, bool VEC2>
+__global__ void __launch_bounds__(256) build_kernel(const BuildArgs a) {
+    __shared__ KParams sP;
+    load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
+    constexpr int NS = (KIND == GPB_GAUSSIAN) ? 7 : 13;
+
+    unsigned need = 0;
+#pragma unroll
+    for (int s = 0; s < NS; s++)
+        if (a.out[s]) need |= 1u << gpb_slice_to_unique(KIND, s);
+
+    const long long j0 = ((long long)blockIdx.x * 32 + threadIdx.x) * 2;
+    if (j0 >= a.cols) return;
+    const bool two = (j0 + 1 < a.cols);
+    const double xa = (j0 < a.n2) ? a.x2[j0] : 0.0;
+    const double xb = (j0 + 1 < a.n2) ? a.x2[j0 + 1] : 0.0;
+    const long long boff = (long long)blockIdx.z * a.bstride;
+
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const long long i = (long long)blockIdx.y * 32 + threadIdx.y + 8 * r;
+        if (i >= a.rows) break;
+        double ua[10], ub[10];
+        const bool vi = i < a.n1;
+        const bool va = vi && (j0 < a.n2), vb = vi && (j0 + 1 < a.n2);
+        if (va | vb) {
+            const double xi = a.x1[i];
+            gpb_eval_unique<KIND>(sP, xi - xa, need, ua);
+            gpb_eval_unique<KIND>(sP, xi - xb, need, ub);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            double* o = a.out[s];
+            if (!o) continue;
+            const int u = gpb_slice_to_unique(KIND, s);
+            double v0 = va ? ua[u] : 0.0, v1 = vb ? ub[u] : 0.0;
+            if (s == 0) {
+                if (a.add_diag) {
+                    if (va && i == j0) v0 += sP.s2;
+                    if (vb && i == j0 + 1) v1 += sP.s2;
+                }
+                if (a.pad_identity) {
+                    if (!va && i == j0) v0 = 1.0;
+                    if (!vb && i == j0 + 1) v1 = 1.0;
+                }
+            }
+            double* p = o + boff + i * a.ld + j0;
+            if (VEC2) {
+                *reinterpret_cast<double2*>(p) = make_double2(v0, v1);   // cols is even when VEC2
+            } else {
+                p[0] = v0;
+                if (two) p[1] = v1;
+            }
+        }
+    }
+}
+
+int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, const double* x1,
+                     long long n1, const double* x2, long long n2, long long rows, long long cols,
+                     double* const* out, long long ld, long long bstride, int add_diag,
+                     int pad_identity, cudaStream_t st) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(rows >= n1 && cols >= n2 && ld >= cols, "bad extents");
+    if (rows == 0 || cols == 0) return GPB_OK;
+    BuildArgs a;
+    if (P) a.P = *P; else memset(&a.P, 0, sizeof(KParams));
+    a.Pb = Pb;
+    a.x1 = x1; a.x2 = x2; a.n1 = n1; a.n2 = n2; a.rows = rows; a.cols = cols;
+    const int ns = gpb_n_slices(kind);
+    bool vec = (ld % 2 == 0) && (cols % 2 == 0) && (bstride % 2 == 0);
+    bool any = false;
+    for (int s = 0; s < GPB_MAX_SLICES; s++) {
+        a.out[s] = (s < ns) ? out[s] : nullptr;
+        if (a.out[s]) {
+            any = true;
+            if (reinterpret_cast<uintptr_t>(a.out[s]) % 16) vec = false;
+        }
+    }
+    if (!any) return GPB_OK;
+    a.ld = ld; a.bstride = bstride; a.add_diag = add_diag; a.pad_identity = pad_identity;
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 31) / 32), (unsigned)batch);
+    GPB_REQUIRE(grid.y <= 65535 && batch <= 65535, "extent too large for the launch grid");
+    if (kind == GPB_GAUSSIAN) {
+        if (vec) build_kernel<GPB_GAUSSIAN, true><<<grid, block, 0, st>>>(a);
+        else build_kernel<GPB_GAUSSIAN, false><<<grid, block, 0, st>>>(a);
+    } else {
+        if (vec) build_kernel<GPB_PERIODIC, true><<<grid, block, 0, st>>>(a);
+        else build_kernel<GPB_PERIODIC, false><<<grid, block, 0, st>>>(a);
+    }
+    GPB_LAUNCH_CHECK("build_kernel");
+    return GPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 2. fused kernel-times-vector: out[g][r] = sum_p coef_p * sum_c slice_p(x1[r], x2[c]) * vec_p[c]
+//    (posterior mean gp.py:597, dm_dtheta gp_c.pyx:122-131, dK_i * alpha for d2lh)
+//    -- the M x N kernel matrix is never written to HBM.
+// ---------------------------------------------------------------------------
+#define GPB_MV_MAXP 8
+#define GPB_MV_MAXO 4
+struct MatvecArgs {
+    KParams P;
+    const KParams* Pb;
+    const double* x1;
+    const double* x2;
+    long long n1, n2;
+    int npairs, nout;
+    int slice[GPB_MV_MAXP];
+    int outidx[GPB_MV_MAXP];
+    double coef[GPB_MV_MAXP];
+    const double* vec[GPB_MV_MAXP];
+    double* out[GPB_MV_MAXO];
+    long long vstride, ostride;   // batch strides of vec / out
+};
+
+// one warp per row, 8 rows per block; lanes stride the columns.
+template <int KIND>
+__global__ void __launch_bounds__(256) fused_matvec_kernel(const MatvecArgs a) {
+    __shared__ KParams sP;
+    load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned need = 0;
+    for (int p = 0; p < a.npairs; p++) need |= 1u << gpb_slice_to_unique(KIND, a.slice[p]);
+    const long long voff = (long long)blockIdx.z * a.vstride;
+    const long long ooff = (long long)blockIdx.z * a.ostride;
+
+    for (long long r = (long long)blockIdx.x * 8 + wid; r < a.n1; r += (long long)gridDim.x * 8) {
+        const double xi = a.x1[r];
+        double acc[GPB_MV_MAXO] = {0, 0, 0, 0};
+        for (long long c = lane; c < a.n2; c += 32) {
+            double u[10];
+            gpb_eval_unique<KIND>(sP, xi - a.x2[c], need, u);
+#pragma unroll
+            for (int p = 0; p < GPB_MV_MAXP; p++) {
+                if (p < a.npairs) {
+                    const double v = gpb_pick(u, gpb_slice_to_unique(KIND, a.slice[p])) * a.vec[p][voff + c];
+                    const double t = a.coef[p] * v;
+#pragma unroll
+                    for (int g = 0; g < GPB_MV_MAXO; g++)
+                        if (a.outidx[p] == g) acc[g] += t;
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < GPB_MV_MAXO; g++) {
+            if (g < a.nout) {
+                const double s = warp_sum(acc[g]);
+                if (lane == 0) a.out[g][ooff + r] = s;
+            }
+        }
+    }
+}
+
+int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int batch,
+                            const double* x1, long long n1, const double* x2, long long n2,
+                            int npairs, const int* slice, const int* outidx, const double* coef,
+                            const double* const* vec, int nout, double* const* out,
+                            long long vstride, long long ostride, cudaStream_t st) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(npairs >= 1 && npairs <= GPB_MV_MAXP && nout >= 1 && nout <= GPB_MV_MAXO, "bad pair count");
+    if (n1 == 0) return GPB_OK;
+    MatvecArgs a;
+    if (P) a.P = *P; else memset(&a.P, 0, sizeof(KParams));
+    a.Pb = Pb; a.x1 = x1; a.x2 = x2; a.n1 = n1; a.n2 = n2; a.npairs = npairs; a.nout = nout;
+    for (int p = 0; p < GPB_MV_MAXP; p++) {
+        a.slice[p] = p < npairs ? slice[p] : 0;
+        a.outidx[p] = p < npairs ? outidx[p] : 0;
+        a.coef[p] = p < npairs ? coef[p] : 0.0;
+        a.vec[p] = p < npairs ? vec[p] : nullptr;
+        if (p < npairs) GPB_REQUIRE(slice[p] >= 0 && slice[p] < gpb_n_slices(kind) && outidx[p] >= 0 && outidx[p] < nout, "bad pair");
+    }
+    for (int g = 0; g < GPB_MV_MAXO; g++) a.out[g] = g < nout ? out[g] : nullptr;
+    a.vstride = vstride; a.ostride = ostride;
+    long long nb = (n1 + 7) / 8;
+    if (nb > 148 * 16) nb = 148 * 16;
+    dim3 grid((unsigned)nb, 1, (unsigned)batch);
+    if (kind == GPB_GAUSSIAN) fused_matvec_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
+    else fused_matvec_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
+    GPB_LAUNCH_CHECK("fused_matvec_kernel");
+    return GPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 3. fused slice reduction over K^-1 (gp_c.pyx:34-49 without the (n_p+1) N^3 GEMMs,
+//    and the trace / quadratic-form terms of gp_c.pyx:104-110):
+//    for every requested slice S_q (q < nsl <= 6, any jacobian or hessian slice):
+//        t0[q] = a^T S_q a ,   t1[q] = sum(Ki o S_q)
+//    plus tr(Ki) and a.a for the noise rows (dK_s = 2 s I).  Slice tiles are
+//    regenerated from x on the fly: one pass over Ki is the only HBM traffic.
+//    Output layout (16 doubles): t0[0..5], t1[0..5], tr(Ki), a.a, 0, 0
+// ---------------------------------------------------------------------------
+#define GPB_RED_MAXS 6
+#define GPB_RED_WIDTH 16
+struct GradArgs {
+    KParams P;
+    const KParams* Pb;
+    const double* x;
+    long long n;            // valid extent (pad rows/cols are excluded)
+    const double* Ki;
+    long long ldk, kstride;
+    const double* alpha;
+    long long astride;
+    double* partial;        // [batch][gridDim.x][16]
+    int nsl;
+    int uq[GPB_RED_MAXS];   // unique slice ids
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const GradArgs a) {
+    __shared__ KParams sP;
+    __shared__ double red[32];
+    load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double* Ki = a.Ki + (long long)blockIdx.z * a.kstride;
+    const double* al = a.alpha + (long long)blockIdx.z * a.astride;
+    unsigned need = 0;
+    for (int q = 0; q < a.nsl; q++) need |= 1u << a.uq[q];
+
+    double t0[GPB_RED_MAXS], t1[GPB_RED_MAXS], tr = 0, aa = 0;
+#pragma unroll
+    for (int q = 0; q < GPB_RED_MAXS; q++) t0[q] = t1[q] = 0.0;
+    for (long long r = (long long)blockIdx.x * 8 + wid; r < a.n; r += (long long)gridDim.x * 8) {
+        const double xi = a.x[r], ar = al[r];
+        const double* row = Ki + r * a.ldk;
+        double q0[GPB_RED_MAXS];
+#pragma unroll
+        for (int q = 0; q < GPB_RED_MAXS; q++) q0[q] = 0.0;
+        for (long long c = lane; c < a.n; c += 32) {
+            double u[10];
+            gpb_eval_unique<KIND>(sP, xi - a.x[c], need, u);
+            const double k = row[c], ac = al[c];
+#pragma unroll
+            for (int q = 0; q < GPB_RED_MAXS; q++) {
+                if (q < a.nsl) {
+                    const double v = gpb_pick(u, a.uq[q]);
+                    q0[q] += v * ac;
+                    t1[q] += v * k;
+                }
+            }
+            if (c == r) tr += k;
+        }
+#pragma unroll
+        for (int q = 0; q < GPB_RED_MAXS; q++) t0[q] += ar * q0[q];
+        if (lane == 0) aa += ar * ar;
+    }
+    double* out = a.partial + ((long long)blockIdx.z * gridDim.x + blockIdx.x) * GPB_RED_WIDTH;
+#pragma unroll
+    for (int q = 0; q < GPB_RED_MAXS; q++) {
+        const double s0 = block_sum(t0[q], red);
+        const double s1 = block_sum(t1[q], red);
+        if (threadIdx.x == 0) { out[q] = s0; out[GPB_RED_MAXS + q] = s1; }
+    }
+    {
+        const double s0 = block_sum(tr, red);
+        const double s1 = block_sum(aa, red);
+        if (threadIdx.x == 0) { out[12] = s0; out[13] = s1; out[14] = 0.0; out[15] = 0.0; }
+    }
+}
+
+// deterministic second stage: out[b][q] = sum_k partial[b][k][q]
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* partial, int nblk, int width, double* out) {
+    __shared__ double red[32];
+    const double* p = partial + (long long)blockIdx.x * nblk * width;
+    for (int q = 0; q < width; q++) {
+        double s = 0;
+        for (int k = threadIdx.x; k < nblk; k += blockDim.x) s += p[(long long)k * width + q];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) out[(long long)blockIdx.x * width + q] = s;
+    }
+}
+
+int gpb_grad_reduce_blocks(long long n) {
+    long long nb = (n + 7) / 8;
+    if (nb > 148 * 4) nb = 148 * 4;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+
+// slices: slice ids (NOT unique ids); nsl <= 6
+int gpb_launch_grad_reduce(int kind, const KParams* P, const KParams* Pb, int batch, const double* x,
+                           long long n, const double* Ki, long long ldk, long long kstride,
+                           const double* alpha, long long astride, int nsl, const int* slices,
+                           double* partial, double* out16, cudaStream_t st) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(nsl >= 0 && nsl <= GPB_RED_MAXS, "at most 6 slices per pass");
+    GradArgs a;
+    if (P) a.P = *P; else memset(&a.P, 0, sizeof(KParams));
+    a.Pb = Pb; a.x = x; a.n = n; a.Ki = Ki; a.ldk = ldk; a.kstride = kstride;
+    a.alpha = alpha; a.astride = astride; a.partial = partial; a.nsl = nsl;
+    for (int q = 0; q < GPB_RED_MAXS; q++) {
+        a.uq[q] = 0;
+        if (q < nsl) {
+            GPB_REQUIRE(slices[q] >= 0 && slices[q] < gpb_n_slices(kind), "bad slice id");
+            a.uq[q] = gpb_slice_to_unique(kind, slices[q]);
+        }
+    }
+    const int nb = gpb_grad_reduce_blocks(n);
+    dim3 grid((unsigned)nb, 1, (unsigned)batch);
+    if (kind == GPB_GAUSSIAN) grad_reduce_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
+    else grad_reduce_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
+    GPB_LAUNCH_CHECK("grad_reduce_kernel");
+    sum_partials_kernel<<<batch, 256, 0, st>>>(partial, nb, GPB_RED_WIDTH, out16);
+    GPB_LAUNCH_CHECK("sum_partials_kernel");
+    return GPB_OK;
+}

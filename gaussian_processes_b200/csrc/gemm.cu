@@ -1,0 +1,179 @@
+// gemm.cu -- the one dense contraction of the GP hot path, on FP64 tensor cores.
+//
+//   C[i,j] = beta * C[i,j] + alpha * sum_{k in [kbeg(i,j), kend(i,j))} A[i,k] * B[j,k]
+//
+// "NT" form: both operands are row-major with the contraction index contiguous,
+// which is exactly the m8n8k4 DMMA fragment layout (A row-major, B "col").  Every
+// O(N^3) step of the path is phrased this way:
+//   TRSM by inverted diagonal block   P_ik = A_ik * W_kk^T
+//   SYRK trailing update              A_ij -= P_ik * P_jk^T           (lower tiles only)
+//   trtri combine                     Tt = V11 * L21^T ;  W21 = -W22 * Tt^T  (+ mirrored V12)
+//   lauum                             Ki = V * V^T                    (lower + mirror)
+//   posterior cov                     Z = Kxox * W^T ;  C = Kxoxo - Z Z^T
+// Triangular operands are exploited at tile granularity through the k-range.
+//
+// Tile 128 x 128 x 16, 256 threads (8 warps as 4 x 2, warp tile 32 x 64 = 4 x 8 DMMA
+// tiles, 64 fp64 accumulators per thread), 4-stage cp.async pipeline (160 KB smem,
+// one CTA per SM).  All extents are multiples of the tile (buffers are padded by the
+// host layer), so there is no edge predication in the main loop.
+#include "common.cuh"
+#include "launch.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int LDS = BK + 4;   // padded row stride (doubles): conflict-free 8-byte fragment loads
+constexpr int TILE_DOUBLES = BM * LDS;
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_DOUBLES * 8;
+
+__device__ __forceinline__ void load_tile(double* sdst, const double* g, long long ld, int tid) {
+    // 128 rows x 16 doubles = 1024 chunks of 16 B; 256 threads x 4
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int c = tid + q * 256;
+        const int row = c >> 3, ch = c & 7;
+        cp_async16(sdst + row * LDS + ch * 2, g + (long long)row * ld + ch * 2);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GpbGemm p) {
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * TILE_DOUBLES;
+
+    // ---- tile coordinates -------------------------------------------------
+    int ti, tj;
+    if (p.lower_only) {
+        // blockIdx.x enumerates lower-triangular tile pairs, longest rows first when
+        // heavy_first (k-range grows with the row for upper-triangular operands)
+        const int t = blockIdx.x;
+        int i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((long long)(i + 1) * (i + 2) / 2 <= t) i++;
+        while ((long long)i * (i + 1) / 2 > t) i--;
+        ti = i;
+        tj = t - i * (i + 1) / 2;
+    } else {
+        ti = blockIdx.x;
+        tj = blockIdx.y;
+    }
+    const int m0 = ti * BM, n0 = tj * BN;
+    const long long bz = blockIdx.z / p.nb1, bt = blockIdx.z % p.nb1;
+    const double* A = p.A + bz * p.sA + bt * p.tA + (long long)m0 * p.lda;
+    const double* B = p.B + bz * p.sB + bt * p.tB + (long long)n0 * p.ldb;
+
+    // ---- k-range from the triangular structure ------------------------------
+    int kbeg = 0, kend = p.K;
+    if (p.a_tri == 1) kend = min(kend, m0 + BM + p.a_off);        // lower: k <= i + off
+    else if (p.a_tri == 2) kbeg = max(kbeg, m0 + p.a_off);        // upper: k >= i + off
+    if (p.b_tri == 1) kend = min(kend, n0 + BN + p.b_off);
+    else if (p.b_tri == 2) kbeg = max(kbeg, n0 + p.b_off);
+    kbeg = max(kbeg, 0) & ~(BK - 1);
+    kend = min((kend + BK - 1) & ~(BK - 1), p.K);
+    const int nk = (kend > kbeg) ? (kend - kbeg) / BK : 0;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm = wid >> 1, wn = wid & 1;          // 4 x 2 warps
+    const int g = lane >> 2, t = lane & 3;
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    // ---- prologue -------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) {
+            load_tile(As + s * TILE_DOUBLES, A + kbeg + s * BK, p.lda, tid);
+            load_tile(Bs + s * TILE_DOUBLES, B + kbeg + s * BK, p.ldb, tid);
+        }
+        cp_async_commit();
+    }
+
+    // ---- main loop --------------------------------------------------------------
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = kt + STAGES - 1;
+            if (nx < nk) {
+                const int slot = nx % STAGES;
+                load_tile(As + slot * TILE_DOUBLES, A + kbeg + nx * BK, p.lda, tid);
+                load_tile(Bs + slot * TILE_DOUBLES, B + kbeg + nx * BK, p.ldb, tid);
+            }
+            cp_async_commit();
+        }
+        const double* as = As + (kt % STAGES) * TILE_DOUBLES + (wm * 32 + g) * LDS + t;
+        const double* bs = Bs + (kt % STAGES) * TILE_DOUBLES + (wn * 64 + g) * LDS + t;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double a[4], b[8];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * LDS + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) b[ni] = bs[ni * 8 * LDS + kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue -----------------------------------------------------------------
+    double* C = p.C + bz * p.sC + bt * p.tC;
+    double* Ct = p.Ct ? p.Ct + bz * p.sCt + bt * p.tCt : nullptr;
+    const bool mirror = (Ct != nullptr) && !(p.lower_only && ti == tj && Ct == C);
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const int r = m0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) {
+            const int c = n0 + wn * 64 + ni * 8 + 2 * t;
+            double2* dst = reinterpret_cast<double2*>(C + (long long)r * p.ldc + c);
+            double v0 = alpha * acc[mi][ni][0], v1 = alpha * acc[mi][ni][1];
+            if (beta != 0.0) {
+                const double2 old = *dst;
+                v0 += beta * old.x;
+                v1 += beta * old.y;
+            }
+            *dst = make_double2(v0, v1);
+            if (mirror) {
+                Ct[(long long)c * p.ldct + r] = v0;
+                Ct[(long long)(c + 1) * p.ldct + r] = v1;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// `batch` = outer batch count; the grid's z extent is batch * p.nb1
+int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st) {
+    GPB_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0, "empty problem");
+    GPB_REQUIRE(p.M % BM == 0 && p.N % BN == 0 && p.K % BK == 0, "extents must be multiples of the 128x128x16 tile");
+    GPB_REQUIRE(p.lda % 2 == 0 && p.ldb % 2 == 0 && p.ldc % 2 == 0, "leading dimensions must be even");
+    GPB_REQUIRE(((uintptr_t)p.A % 16 == 0) && ((uintptr_t)p.B % 16 == 0) && ((uintptr_t)p.C % 16 == 0), "operands must be 16-byte aligned");
+    GPB_REQUIRE(p.sA % 2 == 0 && p.sB % 2 == 0 && p.sC % 2 == 0, "batch strides must be even");
+    GPB_REQUIRE(p.tA % 2 == 0 && p.tB % 2 == 0 && p.tC % 2 == 0 && p.nb1 >= 1, "inner batch strides must be even");
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid;
+    const int tm = p.M / BM, tn = p.N / BN;
+    if (p.lower_only) {
+        GPB_REQUIRE(tm == tn, "lower_only needs a square tile grid");
+        grid = dim3((unsigned)((long long)tm * (tm + 1) / 2), 1, (unsigned)(batch * p.nb1));
+    } else {
+        GPB_REQUIRE(tn <= 65535, "too many column tiles");
+        grid = dim3((unsigned)tm, (unsigned)tn, (unsigned)(batch * p.nb1));
+    }
+    GPB_REQUIRE(batch >= 1 && (long long)batch * p.nb1 <= 65535, "bad batch");
+    gemm_nt_kernel<<<grid, 256, SMEM_BYTES, st>>>(p);
+    GPB_LAUNCH_CHECK("gemm_nt_kernel");
+    return GPB_OK;
+}

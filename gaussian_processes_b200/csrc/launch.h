@@ -1,0 +1,81 @@
+// launch.h -- host-side launchers shared between translation units (internal).
+#pragma once
+#include "common.cuh"
+
+// C = beta*C + alpha * A * B^T over a tile-level k-range (see gemm.cu)
+struct GpbGemm {
+    const double* A;
+    const double* B;
+    double* C;
+    double* Ct;              // optional mirrored (transposed) store, may alias C
+    long long lda, ldb, ldc, ldct;
+    long long sA, sB, sC, sCt;   // outer batch strides (blockIdx.z / nb1: independent GPs / candidates)
+    long long tA, tB, tC, tCt;   // inner batch strides (blockIdx.z % nb1: sibling blocks of one matrix)
+    int nb1;                     // inner batch count (>= 1)
+    int M, N, K;
+    double alpha, beta;
+    int a_tri, b_tri;        // 0 dense | 1 lower (nonzero k <= row + off) | 2 upper (k >= row + off)
+    int a_off, b_off;
+    int lower_only;          // only tiles with tj <= ti (square tile grid); off-diagonal tiles mirrored into Ct
+};
+
+inline GpbGemm gpb_gemm_default() {
+    GpbGemm g;
+    g.A = g.B = nullptr; g.C = g.Ct = nullptr;
+    g.lda = g.ldb = g.ldc = g.ldct = 0;
+    g.sA = g.sB = g.sC = g.sCt = 0;
+    g.tA = g.tB = g.tC = g.tCt = 0;
+    g.nb1 = 1;
+    g.M = g.N = g.K = 0;
+    g.alpha = 1.0; g.beta = 0.0;
+    g.a_tri = g.b_tri = 0; g.a_off = g.b_off = 0;
+    g.lower_only = 0;
+    return g;
+}
+
+int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st);
+
+int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, const double* x1,
+                     long long n1, const double* x2, long long n2, long long rows, long long cols,
+                     double* const* out, long long ld, long long bstride, int add_diag,
+                     int pad_identity, cudaStream_t st);
+
+int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int batch,
+                            const double* x1, long long n1, const double* x2, long long n2,
+                            int npairs, const int* slice, const int* outidx, const double* coef,
+                            const double* const* vec, int nout, double* const* out,
+                            long long vstride, long long ostride, cudaStream_t st);
+
+int gpb_grad_reduce_blocks(long long n);
+int gpb_launch_grad_reduce(int kind, const KParams* P, const KParams* Pb, int batch, const double* x,
+                           long long n, const double* Ki, long long ldk, long long kstride,
+                           const double* alpha, long long astride, int nsl, const int* slices,
+                           double* partial, double* out16, cudaStream_t st);
+
+// potrf.cu
+int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
+                     long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
+                     cudaStream_t st);
+int gpb_launch_trtri(const double* L, long long n, long long ld, long long sL, int batch, double* W,
+                     long long ldw, long long sW, double* V, long long ldv, long long sV, double* T,
+                     long long ldt, long long sT, cudaStream_t st);
+int gpb_launch_lauum(const double* V, long long n, long long ldv, long long sV, int batch, double* Ki,
+                     long long ldk, long long sK, cudaStream_t st);
+int gpb_launch_potrs(const double* L, const double* W, long long n, long long ld, long long ldw,
+                     long long sL, long long sW, int batch, const double* y, long long sy, double* z,
+                     double* alpha, long long svec, int* flags, cudaStream_t st);
+int gpb_launch_loglh(const double* L, long long n_valid, long long ld, long long sL, int batch,
+                     const double* y, long long sy, const double* alpha, long long svec,
+                     const int* info, double* out3, cudaStream_t st);
+int gpb_launch_tril(double* A, long long n, long long ld, long long sA, int batch, cudaStream_t st);
+int gpb_launch_copy2d(double* dst, long long ldd, const double* src, long long lds, long long rows,
+                      long long cols, long long sD, long long sS, int batch, cudaStream_t st);
+
+// reduce.cu
+int gpb_launch_gemv(const double* A, long long rows, long long cols, long long lda, const double* x,
+                    double* y, double alpha, double beta, cudaStream_t st);
+int gpb_launch_trace_prod(const double* A, long long lda, const double* B, long long ldb, long long n,
+                          double* partial, double* out, cudaStream_t st);
+int gpb_launch_quadform(const double* u, const double* M, long long ldm, const double* v, long long n,
+                        double* partial, double* out, cudaStream_t st);
+int gpb_reduce_blocks(long long n);

@@ -1,0 +1,532 @@
+// potrf.cu -- blocked Cholesky of Kxx + s^2 I, the triangular inverse / K^-1 built
+// from it, the Cholesky solves and the log-likelihood reduction.
+//
+// Replaces the LAPACK calls the reference makes through scipy/numpy:
+//   scipy.linalg.cholesky (gp/gp.py:294), cho_solve (gp.py:332-334),
+//   np.linalg.inv + np.dot (gp.py:311-312), np.linalg.slogdet (gp_c.pyx:21).
+//
+// Structure (row-major, lower):  right-looking blocked algorithm with NB = 128.
+//   per block step k:  potrf_diag_kernel   L_kk = chol(A_kk),  W_kk = L_kk^-1, V_kk = W_kk^T
+//                      GEMM (gemm.cu)      A_ik <- A_ik W_kk^T            (TRSM as a DMMA product)
+//                      GEMM                A_ij -= A_ik A_jk^T, i>=j>k    (SYRK, lower tiles)
+//   trtri: pairwise merges  W21 = -W22 (L21 W11), each level one batched GEMM pair
+//   lauum: Ki = V V^T (V = L^-T), one GEMM launch, lower tiles + mirrored store
+// Every kernel carries a batch dimension (independent GPs / MLII candidates).
+#include <vector>
+#include "common.cuh"
+#include "launch.h"
+
+namespace {
+
+// ===========================================================================
+// diagonal-block kernel: one CTA factors and inverts one 128 x 128 block held in
+// shared memory as ten 32 x 32 sub-blocks (lower block-triangle) + ten for W.
+// ===========================================================================
+constexpr int SB = 32;            // sub-block edge
+constexpr int SLD = 36;           // padded stride: 36 = 4 (mod 16) -> conflict-free DMMA fragment loads
+constexpr int SBSZ = SB * SLD;
+constexpr int NBLK = 10;
+constexpr int DLD = 33;           // odd stride for the lane-per-row accesses of the 32x32 factor
+constexpr int DIAG_SMEM = (2 * NBLK * SBSZ + SB * DLD + SB) * 8;
+
+__device__ __forceinline__ int blk(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
+
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ldw, long long sW,
+                  double* V, long long ldv, long long sV, int* info, int col0) {
+    extern __shared__ __align__(16) double sm[];
+    double* Lb = sm;
+    double* Wb = sm + NBLK * SBSZ;
+    double* D = Wb + NBLK * SBSZ;
+    double* invd = D + SB * DLD;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    A += (long long)blockIdx.x * sA;
+    W += (long long)blockIdx.x * sW;
+    if (V) V += (long long)blockIdx.x * sV;
+    info += blockIdx.x;
+
+    // ---- load the lower block-triangle -----------------------------------------
+    for (int bi = 0; bi < 4; bi++)
+        for (int bj = 0; bj <= bi; bj++) {
+            double* dst = Lb + blk(bi, bj) * SBSZ;
+            for (int e = tid; e < SB * SB; e += 256) {
+                const int r = e >> 5, c = e & 31;
+                dst[r * SLD + c] = A[(long long)(bi * SB + r) * ld + bj * SB + c];
+            }
+        }
+    __syncthreads();
+
+    for (int bb = 0; bb < 4; bb++) {
+        // ---- phase 1+2 (warp 0): Cholesky of the 32x32 diagonal sub-block in registers
+        //      (lane i owns row i; pivots/columns travel by warp shuffle), then its inverse.
+        if (wid == 0) {
+            double* Ld = Lb + blk(bb, bb) * SBSZ;
+            for (int r = 0; r < SB; r++) D[r * DLD + lane] = Ld[r * SLD + lane];
+            __syncwarp();
+            double row[SB];
+#pragma unroll
+            for (int k = 0; k < SB; k++) row[k] = D[lane * DLD + k];
+            int fail = 0;
+            double myinv = 0.0;
+#pragma unroll
+            for (int k = 0; k < SB; k++) {
+                const double piv = __shfl_sync(0xffffffffu, row[k], k);
+                if (!(piv > 0.0) && fail == 0) fail = k + 1;       // not positive definite (or NaN)
+                const double d = sqrt(piv);
+                const double id = 1.0 / d;
+                const double lik = (lane == k) ? d : row[k] * id;
+                if (lane == k) myinv = id;
+                row[k] = lik;
+#pragma unroll
+                for (int j = k + 1; j < SB; j++) {
+                    const double ljk = __shfl_sync(0xffffffffu, lik, j);
+                    row[j] = fma(-lik, ljk, row[j]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SB; k++) D[lane * DLD + k] = (k <= lane) ? row[k] : 0.0;
+            invd[lane] = myinv;
+            if (fail && lane == 0 && *info == 0) *info = col0 + bb * SB + fail;
+            __syncwarp();
+            for (int r = 0; r < SB; r++) Ld[r * SLD + lane] = D[r * DLD + lane];
+            // inverse: lane c solves L w = e_c by forward substitution (L rows broadcast from D)
+            double w[SB];
+#pragma unroll
+            for (int r = 0; r < SB; r++) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k + 1 < r; k += 2) {
+                    s0 = fma(D[r * DLD + k], w[k], s0);
+                    s1 = fma(D[r * DLD + k + 1], w[k + 1], s1);
+                }
+                if (r & 1) s0 = fma(D[r * DLD + r - 1], w[r - 1], s0);
+                w[r] = (((r == lane) ? 1.0 : 0.0) - (s0 + s1)) * invd[r];
+            }
+            double* Wd = Wb + blk(bb, bb) * SBSZ;
+#pragma unroll
+            for (int r = 0; r < SB; r++) Wd[r * SLD + lane] = w[r];
+        }
+        __syncthreads();
+
+        const int nbelow = 3 - bb;
+        // ---- phase 3: L_ib = A_ib * W_bb^T for the sub-blocks below (warp owns 8 rows) ----
+        for (int item = wid; item < nbelow * 4; item += 8) {
+            const int bi = bb + 1 + (item >> 2), rt = item & 3;
+            double* Ab = Lb + blk(bi, bb) * SBSZ + (rt * 8 + g) * SLD;
+            const double* Wd = Wb + blk(bb, bb) * SBSZ + g * SLD + t;
+            double acc[4][2];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) acc[ni][0] = acc[ni][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) {
+                const double a = Ab[kk * 4 + t];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[ni][0], acc[ni][1], a, Wd[ni * 8 * SLD + kk * 4]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                Ab[ni * 8 + 2 * t] = acc[ni][0];
+                Ab[ni * 8 + 2 * t + 1] = acc[ni][1];
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 4: trailing update A_ij -= L_ib L_jb^T, bb < j <= i ----------------------
+        const int npairs = nbelow * (nbelow + 1) / 2;
+        for (int item = wid; item < npairs * 16; item += 8) {
+            const int pr = item >> 4, rt = (item >> 2) & 3, ct = item & 3;
+            int ii = 0;
+            while ((ii + 1) * (ii + 2) / 2 <= pr) ii++;
+            const int jj = pr - ii * (ii + 1) / 2;
+            const int bi = bb + 1 + ii, bj = bb + 1 + jj;
+            double* Cb = Lb + blk(bi, bj) * SBSZ + (rt * 8 + g) * SLD + ct * 8 + 2 * t;
+            double c0 = Cb[0], c1 = Cb[1];
+            const double* Ap = Lb + blk(bi, bb) * SBSZ + (rt * 8 + g) * SLD + t;
+            const double* Bp = Lb + blk(bj, bb) * SBSZ + (ct * 8 + g) * SLD + t;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) dmma884(c0, c1, -Ap[kk * 4], Bp[kk * 4]);
+            Cb[0] = c0;
+            Cb[1] = c1;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 5: off-diagonal sub-blocks of W = L^-1, by block distance d ------------
+    //      W_ij = -W_ii * sum_{k=j}^{i-1} L_ik W_kj
+    for (int d = 1; d < 4; d++) {
+        const int nj = 4 - d;
+        for (int item = wid; item < nj * 16; item += 8) {
+            const int j = item >> 4, rt = (item >> 2) & 3, ct = item & 3, i = j + d;
+            double c0 = 0.0, c1 = 0.0;
+            for (int k = j; k < i; k++) {
+                const double* Ap = Lb + blk(i, k) * SBSZ + (rt * 8 + g) * SLD + t;
+                const double* Bp = Wb + blk(k, j) * SBSZ + t * SLD + ct * 8 + g;
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) dmma884(c0, c1, Ap[kk * 4], Bp[kk * 4 * SLD]);
+            }
+            double* Sb = Wb + blk(i, j) * SBSZ + (rt * 8 + g) * SLD + ct * 8 + 2 * t;
+            Sb[0] = c0;
+            Sb[1] = c1;
+        }
+        __syncthreads();
+        for (int item = wid; item < nj * 4; item += 8) {      // warp owns a column tile: in-place safe
+            const int j = item >> 2, ct = item & 3, i = j + d;
+            double acc[4][2];
+#pragma unroll
+            for (int rt = 0; rt < 4; rt++) acc[rt][0] = acc[rt][1] = 0.0;
+            const double* Sp = Wb + blk(i, j) * SBSZ + t * SLD + ct * 8 + g;
+            const double* Wi = Wb + blk(i, i) * SBSZ + g * SLD + t;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) {
+                const double b = Sp[kk * 4 * SLD];
+#pragma unroll
+                for (int rt = 0; rt < 4; rt++) dmma884(acc[rt][0], acc[rt][1], -Wi[rt * 8 * SLD + kk * 4], b);
+            }
+            __syncwarp();
+            double* Ob = Wb + blk(i, j) * SBSZ + g * SLD + ct * 8 + 2 * t;
+#pragma unroll
+            for (int rt = 0; rt < 4; rt++) {
+                Ob[rt * 8 * SLD] = acc[rt][0];
+                Ob[rt * 8 * SLD + 1] = acc[rt][1];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- store L (lower, zero above), W (lower) and V = W^T (upper) ----------------------
+    for (int bi = 0; bi < 4; bi++)
+        for (int bj = 0; bj < 4; bj++) {
+            const bool low = bi >= bj;
+            const double* ls = Lb + (low ? blk(bi, bj) : 0) * SBSZ;
+            const double* ws = Wb + (low ? blk(bi, bj) : 0) * SBSZ;
+            const bool vup = bj >= bi;
+            const double* vs = Wb + (vup ? blk(bj, bi) : 0) * SBSZ;
+            for (int e = tid; e < SB * SB; e += 256) {
+                const int r = e >> 5, c = e & 31;
+                const long long gr = bi * SB + r, gc = bj * SB + c;
+                A[gr * ld + gc] = low ? ls[r * SLD + c] : 0.0;
+                W[gr * ldw + gc] = low ? ws[r * SLD + c] : 0.0;
+                if (V) V[gr * ldv + gc] = vup ? vs[c * SLD + r] : 0.0;
+            }
+        }
+}
+
+// ===========================================================================
+// Cholesky solves with one right-hand side: dataflow over 128-row blocks.
+// CTA i accumulates  sum_j L_ij z_j  as soon as z_j is published (release/acquire
+// flags), then applies the inverted diagonal block.  Tickets make the start order
+// match the dependency order, so spinning CTAs can never starve their producers.
+// ===========================================================================
+constexpr int TS = GPB_NB;
+
+__global__ void __launch_bounds__(256)
+trsv_fwd_kernel(const double* L, long long ld, long long sL, const double* W, long long ldw, long long sW,
+                const double* y, long long sy, double* z, long long svec, int T, int* flags, int* counter) {
+    __shared__ int s_ticket;
+    __shared__ double rhs[TS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(counter, 1);
+    __syncthreads();
+    const int b = s_ticket / T, i = s_ticket % T;
+    L += b * sL; W += b * sW; y += b * sy; z += b * svec; flags += (long long)b * T;
+
+    double acc[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; rr++) acc[rr] = 0.0;
+    for (int j = 0; j < i; j++) {
+        if (tid == 0) while (ld_acquire(flags + j) == 0) {}
+        __syncthreads();
+        const double* zp = z + (long long)j * TS + lane * 4;
+        const double z0 = __ldcg(zp), z1 = __ldcg(zp + 1), z2 = __ldcg(zp + 2), z3 = __ldcg(zp + 3);
+        const double* Lp = L + ((long long)i * TS + wid * 16) * ld + (long long)j * TS + lane * 4;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+            const double2 a = *reinterpret_cast<const double2*>(Lp + rr * ld);
+            const double2 c = *reinterpret_cast<const double2*>(Lp + rr * ld + 2);
+            acc[rr] += a.x * z0 + a.y * z1 + c.x * z2 + c.y * z3;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 16; rr++) {
+        const double s = warp_sum(acc[rr]);
+        if (lane == 0) rhs[wid * 16 + rr] = y[(long long)i * TS + wid * 16 + rr] - s;
+    }
+    __syncthreads();
+    {   // z_i = W_ii * rhs
+        const double r0 = rhs[lane * 4], r1 = rhs[lane * 4 + 1], r2 = rhs[lane * 4 + 2], r3 = rhs[lane * 4 + 3];
+        const double* Wp = W + ((long long)i * TS + wid * 16) * ldw + (long long)i * TS + lane * 4;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+            const double2 a = *reinterpret_cast<const double2*>(Wp + rr * ldw);
+            const double2 c = *reinterpret_cast<const double2*>(Wp + rr * ldw + 2);
+            const double s = warp_sum(a.x * r0 + a.y * r1 + c.x * r2 + c.y * r3);
+            if (lane == 0) z[(long long)i * TS + wid * 16 + rr] = s;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(flags + i, 1);
+}
+
+__global__ void __launch_bounds__(256)
+trsv_bwd_kernel(const double* L, long long ld, long long sL, const double* W, long long ldw, long long sW,
+                const double* z, double* alpha, long long svec, int T, int* flags, int* counter) {
+    __shared__ int s_ticket;
+    __shared__ double rhs[TS];
+    __shared__ double red[8][TS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(counter, 1);
+    __syncthreads();
+    const int b = s_ticket / T, i = T - 1 - (s_ticket % T);
+    L += b * sL; W += b * sW; z += b * svec; alpha += b * svec; flags += (long long)b * T;
+
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = T - 1; j > i; j--) {
+        if (tid == 0) while (ld_acquire(flags + j) == 0) {}
+        __syncthreads();
+        const double* ap = alpha + (long long)j * TS + wid * 16;
+        const double* Lp = L + ((long long)j * TS + wid * 16) * ld + (long long)i * TS + lane * 4;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+            const double ar = __ldcg(ap + rr);
+            const double2 a = *reinterpret_cast<const double2*>(Lp + rr * ld);
+            const double2 c = *reinterpret_cast<const double2*>(Lp + rr * ld + 2);
+            acc[0] += a.x * ar; acc[1] += a.y * ar; acc[2] += c.x * ar; acc[3] += c.y * ar;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) red[wid][lane * 4 + q] = acc[q];
+    __syncthreads();
+    if (tid < TS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += red[w][tid];
+        rhs[tid] = z[(long long)i * TS + tid] - s;
+    }
+    __syncthreads();
+    {   // alpha_i = W_ii^T * rhs
+        double a4[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* Wp = W + ((long long)i * TS + wid * 16) * ldw + (long long)i * TS + lane * 4;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+            const double rv = rhs[wid * 16 + rr];
+            const double2 a = *reinterpret_cast<const double2*>(Wp + rr * ldw);
+            const double2 c = *reinterpret_cast<const double2*>(Wp + rr * ldw + 2);
+            a4[0] += a.x * rv; a4[1] += a.y * rv; a4[2] += c.x * rv; a4[3] += c.y * rv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) red[wid][lane * 4 + q] = a4[q];
+    }
+    __syncthreads();
+    if (tid < TS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += red[w][tid];
+        alpha[(long long)i * TS + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(flags + i, 1);
+}
+
+// log_lh = -1/2 y.alpha - 1/2 logdet - n/2 log 2pi  with the reference's clamps
+// (gp_c.pyx:21-29: -inf when logdet < MIN; gp.py:362-365: -inf when not PD).
+// logdet comes from the Cholesky diagonal -- no second (LU) factorisation.
+__global__ void __launch_bounds__(256)
+loglh_kernel(const double* L, long long n, long long ld, long long sL, const double* y, long long sy,
+             const double* alpha, long long svec, const int* info, double* out3) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    L += b * sL; y += b * sy; alpha += b * svec;
+    double sl = 0.0, sq = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        sl += log(L[i * ld + i]);
+        sq += y[i] * alpha[i];
+    }
+    sl = block_sum(sl, red);
+    sq = block_sum(sq, red);
+    if (threadIdx.x == 0) {
+        const double logdet = 2.0 * sl;
+        double llh;
+        if ((info && info[b] != 0) || logdet < GPB_MIN_LOG) llh = -INFINITY;
+        else llh = -0.5 * sq + -0.5 * logdet + -0.5 * (double)n * log(2.0 * M_PI);
+        out3[b * 3 + 0] = llh;
+        out3[b * 3 + 1] = logdet;
+        out3[b * 3 + 2] = sq;
+    }
+}
+
+__global__ void tril_kernel(double* A, long long n, long long ld, long long sA) {
+    A += (long long)blockIdx.z * sA;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    if (r < n && c < n && c > r) A[r * ld + c] = 0.0;
+}
+
+__global__ void copy2d_kernel(double* dst, long long ldd, const double* src, long long lds,
+                              long long rows, long long cols, long long sD, long long sS) {
+    dst += (long long)blockIdx.z * sD;
+    src += (long long)blockIdx.z * sS;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y; r < rows;
+         r += (long long)gridDim.y * blockDim.y)
+        if (c < cols) dst[r * ldd + c] = src[r * lds + c];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// drivers
+// ---------------------------------------------------------------------------
+int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
+                     long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
+                     cudaStream_t st) {
+    GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
+    GPB_REQUIRE(ld >= n && ldw >= n && (!V || ldv >= n), "leading dimension too small");
+    GPB_REQUIRE(A && W && info, "null pointer");
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+        attr_set = true;
+    }
+    GPB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+    const int T = (int)(n / GPB_NB);
+    for (int k = 0; k < T; k++) {
+        const long long o = (long long)k * GPB_NB;
+        potrf_diag_kernel<<<batch, 256, DIAG_SMEM, st>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
+                                                         V ? V + o * ldv + o : nullptr, ldv, sV, info,
+                                                         (int)o);
+        GPB_LAUNCH_CHECK("potrf_diag_kernel");
+        const int rem = (T - 1 - k) * GPB_NB;
+        if (rem == 0) break;
+        GpbGemm g = gpb_gemm_default();            // panel: A_ik <- A_ik * W_kk^T (in place)
+        g.A = A + (o + GPB_NB) * ld + o; g.lda = ld; g.sA = sA;
+        g.B = W + o * ldw + o; g.ldb = ldw; g.sB = sW;
+        g.C = A + (o + GPB_NB) * ld + o; g.ldc = ld; g.sC = sA;
+        g.M = rem; g.N = GPB_NB; g.K = GPB_NB;
+        g.b_tri = 1;                               // W_kk lower: k <= j
+        int stt = gpb_launch_gemm(g, batch, st);
+        if (stt != GPB_OK) return stt;
+        GpbGemm u = gpb_gemm_default();            // trailing: A_ij -= P_i P_j^T (lower tiles)
+        u.A = g.C; u.lda = ld; u.sA = sA;
+        u.B = g.C; u.ldb = ld; u.sB = sA;
+        u.C = A + (o + GPB_NB) * ld + (o + GPB_NB); u.ldc = ld; u.sC = sA;
+        u.M = rem; u.N = rem; u.K = GPB_NB;
+        u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+        stt = gpb_launch_gemm(u, batch, st);
+        if (stt != GPB_OK) return stt;
+    }
+    return GPB_OK;
+}
+
+// W = L^-1 (lower) and V = W^T (upper) from the inverted 128-blocks left by potrf.
+// Adjacent blocks are merged pairwise; all equal-sized pairs of a level share one launch.
+int gpb_launch_trtri(const double* L, long long n, long long ld, long long sL, int batch, double* W,
+                     long long ldw, long long sW, double* V, long long ldv, long long sV, double* T,
+                     long long ldt, long long sT, cudaStream_t st) {
+    GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
+    GPB_REQUIRE(L && W && V && T, "null pointer");
+    std::vector<long long> bounds;
+    for (long long b = 0; b <= n; b += GPB_NB) bounds.push_back(b);
+    while (bounds.size() > 2) {
+        std::vector<long long> nb;
+        const size_t npairs = (bounds.size() - 1) / 2;
+        size_t p = 0;
+        while (p < npairs) {
+            const long long lo = bounds[2 * p], mid = bounds[2 * p + 1], hi = bounds[2 * p + 2];
+            const long long n1 = mid - lo, n2 = hi - mid;
+            size_t q = p + 1;     // extend over following pairs with the same shape
+            while (q < npairs && bounds[2 * q + 1] - bounds[2 * q] == n1 &&
+                   bounds[2 * q + 2] - bounds[2 * q + 1] == n2 && bounds[2 * q] - bounds[2 * (q - 1)] == n1 + n2)
+                q++;
+            const int cnt = (int)(q - p);
+            const long long step = n1 + n2;
+            // Tt[c, r] = sum_j V11[c, j] L21[r, j]      (c in block 1, r in block 2)
+            GpbGemm g = gpb_gemm_default();
+            g.A = V + lo * ldv + lo; g.lda = ldv; g.sA = sV; g.tA = step * (ldv + 1);
+            g.B = L + mid * ld + lo; g.ldb = ld; g.sB = sL; g.tB = step * (ld + 1);
+            g.C = T + lo * ldt + mid; g.ldc = ldt; g.sC = sT; g.tC = step * (ldt + 1);
+            g.M = (int)n1; g.N = (int)n2; g.K = (int)n1; g.a_tri = 2; g.nb1 = cnt;
+            int stt = gpb_launch_gemm(g, batch, st);
+            if (stt != GPB_OK) return stt;
+            // W21[r, c] = -sum_q W22[r, q] Tt[c, q]   and the mirrored V12[c, r]
+            GpbGemm h = gpb_gemm_default();
+            h.A = W + mid * ldw + mid; h.lda = ldw; h.sA = sW; h.tA = step * (ldw + 1);
+            h.B = g.C; h.ldb = ldt; h.sB = sT; h.tB = step * (ldt + 1);
+            h.C = W + mid * ldw + lo; h.ldc = ldw; h.sC = sW; h.tC = step * (ldw + 1);
+            h.Ct = V + lo * ldv + mid; h.ldct = ldv; h.sCt = sV; h.tCt = step * (ldv + 1);
+            h.M = (int)n2; h.N = (int)n1; h.K = (int)n2; h.a_tri = 1; h.alpha = -1.0; h.nb1 = cnt;
+            stt = gpb_launch_gemm(h, batch, st);
+            if (stt != GPB_OK) return stt;
+            p = q;
+        }
+        for (size_t i = 0; i + 2 < bounds.size(); i += 2) nb.push_back(bounds[i]);
+        if ((bounds.size() - 1) % 2 == 1) nb.push_back(bounds[bounds.size() - 2]);
+        nb.push_back(bounds.back());
+        bounds.swap(nb);
+    }
+    return GPB_OK;
+}
+
+// Ki = V V^T = L^-T L^-1  (the reference's inv(L).T @ inv(L), gp.py:311-312)
+int gpb_launch_lauum(const double* V, long long n, long long ldv, long long sV, int batch, double* Ki,
+                     long long ldk, long long sK, cudaStream_t st) {
+    GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
+    GpbGemm g = gpb_gemm_default();
+    g.A = V; g.lda = ldv; g.sA = sV;
+    g.B = V; g.ldb = ldv; g.sB = sV;
+    g.C = Ki; g.ldc = ldk; g.sC = sK;
+    g.Ct = Ki; g.ldct = ldk; g.sCt = sK;
+    g.M = g.N = g.K = (int)n;
+    g.a_tri = 2; g.b_tri = 2; g.lower_only = 1;
+    return gpb_launch_gemm(g, batch, st);
+}
+
+// alpha = K^-1 y by forward + backward substitution (cho_solve, gp.py:332-334).
+// flags: int workspace of at least 2 * batch * T + 2 entries.
+int gpb_launch_potrs(const double* L, const double* W, long long n, long long ld, long long ldw,
+                     long long sL, long long sW, int batch, const double* y, long long sy, double* z,
+                     double* alpha, long long svec, int* flags, cudaStream_t st) {
+    GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
+    GPB_REQUIRE(ld % 2 == 0 && ldw % 2 == 0 && sL % 2 == 0 && sW % 2 == 0, "strides must be even");
+    const int T = (int)(n / GPB_NB);
+    const size_t nfl = (size_t)2 * batch * T + 2;
+    GPB_CUDA(cudaMemsetAsync(flags, 0, nfl * sizeof(int), st));
+    int* fF = flags + 2;
+    int* fB = fF + (size_t)batch * T;
+    trsv_fwd_kernel<<<batch * T, 256, 0, st>>>(L, ld, sL, W, ldw, sW, y, sy, z, svec, T, fF, flags);
+    GPB_LAUNCH_CHECK("trsv_fwd_kernel");
+    trsv_bwd_kernel<<<batch * T, 256, 0, st>>>(L, ld, sL, W, ldw, sW, z, alpha, svec, T, fB, flags + 1);
+    GPB_LAUNCH_CHECK("trsv_bwd_kernel");
+    return GPB_OK;
+}
+
+int gpb_launch_loglh(const double* L, long long n_valid, long long ld, long long sL, int batch,
+                     const double* y, long long sy, const double* alpha, long long svec,
+                     const int* info, double* out3, cudaStream_t st) {
+    loglh_kernel<<<batch, 256, 0, st>>>(L, n_valid, ld, sL, y, sy, alpha, svec, info, out3);
+    GPB_LAUNCH_CHECK("loglh_kernel");
+    return GPB_OK;
+}
+
+int gpb_launch_tril(double* A, long long n, long long ld, long long sA, int batch, cudaStream_t st) {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 7) / 8), (unsigned)batch);
+    tril_kernel<<<grid, block, 0, st>>>(A, n, ld, sA);
+    GPB_LAUNCH_CHECK("tril_kernel");
+    return GPB_OK;
+}
+
+int gpb_launch_copy2d(double* dst, long long ldd, const double* src, long long lds, long long rows,
+                      long long cols, long long sD, long long sS, int batch, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return GPB_OK;
+    dim3 block(32, 8);
+    long long gy = (rows + 7) / 8;
+    if (gy > 16384) gy = 16384;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)gy, (unsigned)batch);
+    copy2d_kernel<<<grid, block, 0, st>>>(dst, ldd, src, lds, rows, cols, sD, sS);
+    GPB_LAUNCH_CHECK("copy2d_kernel");
+    return GPB_OK;
+}

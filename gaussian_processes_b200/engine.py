@@ -1,0 +1,366 @@
+"""Device-resident state of one GP and every computation of the hot path, expressed as
+calls into libgpb200.so on torch-owned HBM buffers.
+
+Nothing here computes on the CPU: torch allocates, ctypes launches, and host values
+appear only when a scalar / small vector (or a matrix the user asked for) is read back.
+Matrices are padded to a multiple of 128 with an identity pad (DESIGN.md "Data layout"),
+so the factor of the padded matrix is [[L, 0], [0, I]] and every pad contribution to
+log-determinants, traces and quadratic forms is exactly zero.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, device as D
+from ._lib import call, darr, iarr, parr
+
+GAUSSIAN, PERIODIC = 0, 1
+N_KP = {GAUSSIAN: 2, PERIODIC: 3}
+DTYPE = np.float64
+MIN = float(np.log(np.exp2(DTYPE(np.finfo(DTYPE).minexp + 4))))   # gp.py:17
+
+
+def jac_slices(kind):
+    return list(range(1, 1 + N_KP[kind]))
+
+
+def hess_slice(kind, i, j):
+    n_p = N_KP[kind]
+    return 1 + n_p + i * n_p + j
+
+
+class Engine(object):
+    """One (kernel, theta, s, x, y) on the device; results are cached until dropped."""
+
+    def __init__(self, kind, kparams, s, x, y):
+        self.kind = int(kind)
+        self.n_p = N_KP[self.kind]
+        self.kparams = [float(v) for v in kparams]
+        self.s = float(s)
+        self.n = int(np.asarray(x).size)
+        self.npad = D.roundup(self.n)
+        self.T = self.npad // D.NB
+        self.dx = D.to_device(x)
+        self.dy = D.to_device(y, pad_to=self.npad)
+        self.finite = bool(np.isfinite(np.asarray(x)).all() and np.isfinite(np.asarray(y)).all())
+        self._c = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _theta(self):
+        return darr(self.kparams)
+
+    def _partial(self):
+        if "partial" not in self._c:
+            self._c["partial"] = D.empty(int(_lib.lib.gpb_grad_partial_doubles(self.n)) + 1024)
+        return self._c["partial"]
+
+    def build(self, x1, n1, x2, n2, rows, cols, mask, add_diag=False, pad_identity=False, out=None):
+        """Selected slices of the kernel between device vectors x1, x2 -> [nsel, rows, cols]."""
+        nsel = bin(mask).count("1")
+        if out is None:
+            out = D.empty(nsel, rows, cols)
+        call("gpb_kernel_build", self.kind, self._theta(), self.s, D.ptr(x1), n1, D.ptr(x2), n2, rows,
+             cols, mask, D.ptr(out), cols, rows * cols, int(add_diag), int(pad_identity), D.stream_ptr())
+        return out
+
+    def gemm(self, A, B, C, M, N, K, alpha=1.0, beta=0.0, a_tri=0, b_tri=0, lower_only=0, Ct=None):
+        call("gpb_gemm_nt", D.ptr(A), A.stride(-2), D.ptr(B), B.stride(-2), D.ptr(C), C.stride(-2),
+             D.ptr(Ct), Ct.stride(-2) if Ct is not None else 0, M, N, K, alpha, beta, a_tri, b_tri,
+             lower_only, D.stream_ptr())
+        return C
+
+    def gemv(self, A, rows, cols, x, y=None, alpha=1.0, beta=0.0):
+        if y is None:
+            y = D.empty(rows)
+        call("gpb_gemv", D.ptr(A), rows, cols, A.stride(-2) if A.dim() > 1 else cols, D.ptr(x), D.ptr(y),
+             alpha, beta, D.stream_ptr())
+        return y
+
+    def dot(self, u, v, n):
+        """u . v via a 1-row GEMV (device scalar tensor)."""
+        out = D.empty(1)
+        call("gpb_gemv", D.ptr(u), 1, n, n, D.ptr(v), D.ptr(out), 1.0, 0.0, D.stream_ptr())
+        return out
+
+    # ------------------------------------------------------------------ Kxx and its factor
+    def Kxx(self):
+        """Kxx + s^2 I (index diagonal, gp.py:265) on the device, [npad, npad] identity-padded."""
+        if "K" not in self._c:
+            self._c["K"] = self.build(self.dx, self.n, self.dx, self.n, self.npad, self.npad, 1,
+                                      add_diag=True, pad_identity=True)[0]
+        return self._c["K"]
+
+    def factor(self):
+        """Blocked Cholesky (gp.py:294).  Returns LAPACK-style info (0 = ok)."""
+        if "info" not in self._c:
+            n = self.npad
+            if "K" in self._c:
+                L = self._c["K"].clone()
+            else:   # build straight into the factorisation buffer: no extra pass over HBM
+                L = self.build(self.dx, self.n, self.dx, self.n, n, n, 1, add_diag=True, pad_identity=True)[0]
+            W, V = D.empty(n, n), D.empty(n, n)
+            info = D.izeros(1)
+            call("gpb_potrf", D.ptr(L), n, n, 0, 1, D.ptr(W), n, 0, D.ptr(V), n, 0, D.ptr(info), D.stream_ptr())
+            self._c.update(L=L, W=W, V=V, info=int(info.item()))
+        return self._c["info"]
+
+    def require_pd(self):
+        if not self.finite:
+            # scipy.linalg.cholesky(check_finite=True) at gp.py:294
+            raise ValueError("array must not contain infs or NaNs")
+        info = self.factor()
+        if info != 0:
+            raise np.linalg.LinAlgError(
+                "%d-th leading minor of the array is not positive definite" % info)
+
+    def Lxx_host(self):
+        self.require_pd()
+        L = self._c["L"].clone()
+        call("gpb_tril", D.ptr(L), self.npad, self.npad, D.stream_ptr())
+        return D.to_host(L[:self.n, :self.n]).copy()
+
+    def alpha(self):
+        """K^-1 y by forward/backward substitution (cho_solve, gp.py:332-334); [npad], pad = 0."""
+        self.require_pd()
+        if "alpha" not in self._c:
+            n = self.npad
+            z, a = D.empty(n), D.empty(n)
+            flags = D.izeros(2 * self.T + 2)
+            call("gpb_potrs", D.ptr(self._c["L"]), D.ptr(self._c["W"]), n, n, n, 0, 0, 1, D.ptr(self.dy), 0,
+                 D.ptr(z), D.ptr(a), n, D.ptr(flags), D.stream_ptr())
+            self._c["alpha"] = a
+        return self._c["alpha"]
+
+    def inv_factor(self):
+        """W = L^-1 (lower) and V = L^-T (upper), completed from potrf's diagonal blocks."""
+        self.require_pd()
+        if "trtri" not in self._c:
+            n = self.npad
+            T = self._c.get("Ki_buf")
+            if T is None:
+                T = self._c["Ki_buf"] = D.empty(n, n)
+            call("gpb_trtri", D.ptr(self._c["L"]), n, n, 0, 1, D.ptr(self._c["W"]), n, 0,
+                 D.ptr(self._c["V"]), n, 0, D.ptr(T), n, 0, D.stream_ptr())
+            self._c["trtri"] = True
+        return self._c["W"], self._c["V"]
+
+    def Ki(self):
+        """inv(L)^T inv(L) (gp.py:311-312), full symmetric [npad, npad]."""
+        if "Ki" not in self._c:
+            _, V = self.inv_factor()
+            n = self.npad
+            Ki = self._c["Ki_buf"]
+            call("gpb_lauum", D.ptr(V), n, n, 0, 1, D.ptr(Ki), n, 0, D.stream_ptr())
+            self._c["Ki"] = Ki
+        return self._c["Ki"]
+
+    # ------------------------------------------------------------------ likelihood
+    def loglh3(self):
+        """(log_lh, logdet, y.alpha) -- gp_c.log_lh (gp_c.pyx:17-31) with logdet from the Cholesky."""
+        if "loglh3" not in self._c:
+            a = self.alpha()
+            out = D.empty(3)
+            info = D.izeros(1)
+            call("gpb_loglh", D.ptr(self._c["L"]), self.n, self.npad, D.ptr(self.dy), D.ptr(a), D.ptr(info),
+                 D.ptr(out), D.stream_ptr())
+            self._c["loglh3"] = tuple(float(v) for v in D.to_host(out))
+        return self._c["loglh3"]
+
+    def slice_reduce(self, slices):
+        """For each slice S: (alpha^T S alpha, sum(Ki o S)); plus tr(Ki) and alpha.alpha."""
+        Ki, a = self.Ki(), self.alpha()
+        t0, t1 = [], []
+        tr = aa = None
+        for lo in range(0, max(len(slices), 1), 6):
+            chunk = list(slices[lo:lo + 6])
+            out = D.empty(16)
+            call("gpb_slice_reduce", self.kind, self._theta(), D.ptr(self.dx), self.n, D.ptr(Ki), self.npad,
+                 D.ptr(a), len(chunk), iarr(chunk + [0]), D.ptr(self._partial()), D.ptr(out), D.stream_ptr())
+            h = D.to_host(out)
+            t0 += list(h[:len(chunk)])
+            t1 += list(h[6:6 + len(chunk)])
+            tr, aa = float(h[12]), float(h[13])
+        return np.array(t0), np.array(t1), tr, aa
+
+    def grad_terms(self):
+        """t0[i] = y^T Ki dK_i Ki y, t1[i] = tr(Ki dK_i) for the kernel params and s (gp_c.pyx:41-49)."""
+        if "grad_terms" not in self._c:
+            t0, t1, tr, aa = self.slice_reduce(jac_slices(self.kind))
+            t0 = np.append(t0, 2.0 * self.s * aa)        # dK_s = 2 s I  (gp_c.pyx:45)
+            t1 = np.append(t1, 2.0 * self.s * tr)
+            self._c["grad_terms"] = (t0, t1)
+        return self._c["grad_terms"]
+
+    # ------------------------------------------------------------------ second derivatives
+    def d2_terms(self):
+        """Everything gp_c.d2lh_dtheta2 (gp_c.pyx:70-111) needs, as [n_theta, n_theta] arrays:
+        G[i,j] = b_j . Ki b_i (b_i = dK_i alpha), Q[i,j] = alpha^T d2K_ij alpha,
+        TP[i,j] = tr(Ki dK_j Ki dK_i), TH[i,j] = tr(Ki d2K_ij)."""
+        if "d2" in self._c:
+            return self._c["d2"]
+        n, npad, n_p, s = self.n, self.npad, self.n_p, self.s
+        nth = n_p + 1
+        Ki, a = self.Ki(), self.alpha()
+        st = D.stream_ptr()
+        # b_i = dK_i alpha (kernel tiles regenerated on the fly); b_s = 2 s alpha
+        B = D.zeros(nth, npad)
+        sl = jac_slices(self.kind)
+        call("gpb_kernel_matvec", self.kind, self._theta(), D.ptr(self.dx), n, D.ptr(self.dx), n, n_p,
+             iarr(sl), iarr(range(n_p)), darr([1.0] * n_p), parr([D.ptr(a)] * n_p), n_p,
+             parr([B[i].data_ptr() for i in range(n_p)]), st)
+        # c_i = Ki b_i
+        C = D.zeros(nth, npad)
+        for i in range(n_p):
+            self.gemv(Ki, n, n, B[i], C[i])
+        Kia = self.gemv(Ki, n, n, a)                       # Ki alpha, for the s row
+        Gd = D.empty(nth, nth)
+        for i in range(n_p):
+            # column over j of b_j . c_i  (the s row/column is assembled from Kia below)
+            call("gpb_gemv", D.ptr(B), n_p, n, npad, D.ptr(C[i]), D.ptr(Gd[i]), 1.0, 0.0, st)
+        bs_ci = [self.dot(a, C[i], n) for i in range(n_p)]           # alpha . c_i
+        bj_kia = [self.dot(B[j], Kia, n) for j in range(n_p)]        # b_j . Ki alpha
+        a_kia = self.dot(a, Kia, n)
+        # P_i = Ki dK_i (dense products on the DMMA GEMM), then traces of products
+        J = self.build(self.dx, n, self.dx, n, npad, npad, sum(1 << q for q in sl))
+        P = D.empty(n_p, npad, npad)
+        for i in range(n_p):
+            self.gemm(Ki, J[i], P[i], npad, npad, npad)
+        tp = D.empty(nth * nth + 1)
+        part = self._partial()
+
+        def trace_prod(A, Bm, slot):
+            call("gpb_trace_prod", D.ptr(A), npad, D.ptr(Bm), npad, n, D.ptr(part), tp[slot:].data_ptr(), st)
+        for i in range(n_p):
+            for j in range(n_p):
+                trace_prod(P[j], P[i], i * nth + j)
+            trace_prod(Ki, P[i], i * nth + n_p)
+        trace_prod(Ki, Ki, nth * nth - 1)
+        # Hessian slices: alpha^T H alpha and sum(Ki o H)
+        pairs = [(i, j) for i in range(n_p) for j in range(i, n_p)]
+        q0, q1, tr, aa = self.slice_reduce([hess_slice(self.kind, i, j) for i, j in pairs])
+        Gh = D.to_host(Gd)
+        tph = D.to_host(tp)
+        G = np.zeros((nth, nth))
+        Q = np.zeros((nth, nth))
+        TP = np.zeros((nth, nth))
+        TH = np.zeros((nth, nth))
+        for i in range(n_p):
+            for j in range(n_p):
+                G[i, j] = Gh[i, j]
+                TP[i, j] = tph[i * nth + j]
+            G[i, n_p] = 2 * s * float(bs_ci[i].item())          # b_s . c_i
+            G[n_p, i] = 2 * s * float(bj_kia[i].item())         # b_i . c_s
+            TP[i, n_p] = TP[n_p, i] = 2 * s * tph[i * nth + n_p]
+        G[n_p, n_p] = 4 * s * s * float(a_kia.item())
+        TP[n_p, n_p] = 4 * s * s * tph[nth * nth - 1]
+        for (i, j), v0, v1 in zip(pairs, q0, q1):
+            Q[i, j] = Q[j, i] = v0
+            TH[i, j] = TH[j, i] = v1
+        Q[n_p, n_p] = 2.0 * aa                                  # d2k = 2 I (gp_c.pyx:99-100)
+        TH[n_p, n_p] = 2.0 * tr
+        self._c["d2"] = (G, Q, TP, TH)
+        return self._c["d2"]
+
+    # ------------------------------------------------------------------ posterior
+    def mean(self, xo):
+        """K(xo, x) alpha without materialising K(xo, x) (gp.py:597)."""
+        a = self.alpha()
+        m = int(xo.size)
+        dxo = D.to_device(xo)
+        out = D.empty(max(m, 1))
+        if m:
+            call("gpb_kernel_matvec", self.kind, self._theta(), D.ptr(dxo), m, D.ptr(self.dx), self.n, 1,
+                 iarr([0]), iarr([0]), darr([1.0]), parr([D.ptr(a)]), 1, parr([D.ptr(out)]), D.stream_ptr())
+        return D.to_host(out[:m]).copy()
+
+    def cov(self, xo):
+        """K(xo,xo) - K(xo,x) K^-1 K(x,xo) as Kxoxo - Z Z^T with Z = K(xo,x) L^-T (gp.py:599-625)."""
+        W, _ = self.inv_factor()
+        m = int(xo.size)
+        if m == 0:
+            return np.empty((0, 0), dtype=DTYPE)
+        mp = D.roundup(m)
+        dxo = D.to_device(xo)
+        Kxox = self.build(dxo, m, self.dx, self.n, mp, self.npad, 1)[0]
+        Z = D.empty(mp, self.npad)
+        self.gemm(Kxox, W, Z, mp, self.npad, self.npad, b_tri=1)
+        C = self.build(dxo, m, dxo, m, mp, mp, 1)[0]
+        self.gemm(Z, Z, C, mp, mp, self.npad, alpha=-1.0, beta=1.0, lower_only=1, Ct=C)
+        return D.to_host(C[:m, :m]).copy()
+
+    def dm(self, xo):
+        """gp_c.dm_dtheta (gp_c.pyx:114-131) with mat-vecs only:
+        dm[i] = dK_i(xo,x) alpha - K(xo,x) Ki (dK_i alpha);  s row: -K(xo,x) Ki (2 s alpha)."""
+        n, npad, n_p = self.n, self.npad, self.n_p
+        nth = n_p + 1
+        Ki, a = self.Ki(), self.alpha()
+        st = D.stream_ptr()
+        m = int(xo.size)
+        sl = jac_slices(self.kind)
+        B = D.zeros(n_p, npad)
+        call("gpb_kernel_matvec", self.kind, self._theta(), D.ptr(self.dx), n, D.ptr(self.dx), n, n_p,
+             iarr(sl), iarr(range(n_p)), darr([1.0] * n_p), parr([D.ptr(a)] * n_p), n_p,
+             parr([B[i].data_ptr() for i in range(n_p)]), st)
+        C = D.zeros(nth, npad)
+        for i in range(n_p):
+            self.gemv(Ki, n, n, B[i], C[i])
+        self.gemv(Ki, n, n, a, C[n_p])
+        out = D.zeros(nth, max(m, 1))
+        if m:
+            dxo = D.to_device(xo)
+            slices = sl + [0] * nth
+            outidx = list(range(n_p)) + list(range(nth))
+            coef = [1.0] * n_p + [-1.0] * n_p + [-2.0 * self.s]
+            vecs = [D.ptr(a)] * n_p + [C[i].data_ptr() for i in range(nth)]
+            call("gpb_kernel_matvec", self.kind, self._theta(), D.ptr(dxo), m, D.ptr(self.dx), n, len(slices),
+                 iarr(slices), iarr(outidx), darr(coef), parr(vecs), nth,
+                 parr([out[i].data_ptr() for i in range(nth)]), st)
+        return D.to_host(out[:, :m]).copy()
+
+
+# ---------------------------------------------------------------------------
+# batched evaluation: log_lh + dloglh_dtheta for many hyperparameter candidates
+# ---------------------------------------------------------------------------
+class BatchEvaluator(object):
+    """Fixed (x, y) on the device; evaluates chunks of theta candidates through the
+    fused C-ABI evaluator ``gpb_gp_eval`` (one workspace, reused)."""
+
+    def __init__(self, kind, x, y, max_batch=None, workspace_gb=24.0):
+        self.kind = int(kind)
+        self.nth = N_KP[self.kind] + 1
+        self.n = int(np.asarray(x).size)
+        self.dx = D.to_device(x)
+        self.dy = D.to_device(y)
+        per = int(_lib.lib.gpb_eval_workspace_bytes(self.n, 1, 1))
+        cap = max(1, int(workspace_gb * 2 ** 30) // per)
+        self.max_batch = int(min(cap, max_batch or cap, 65535 // max(1, D.roundup(self.n) // D.NB)))
+        self._ws = None
+        self._ws_batch = 0
+
+    def _workspace(self, batch, want_grad):
+        if self._ws is None or batch > self._ws_batch:
+            nbytes = int(_lib.lib.gpb_eval_workspace_bytes(self.n, batch, 1))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=D.require_cuda())
+            self._ws_batch = batch
+        return self._ws
+
+    def eval_device(self, thetas, want_grad=True):
+        """thetas: host [B, n_theta].  Returns the device tensor [B, 8]:
+        log_lh, dloglh[0..3], logdet, y.alpha, info."""
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        B = thetas.shape[0]
+        res = D.empty(B, 8)
+        for lo in range(0, B, self.max_batch):
+            hi = min(B, lo + self.max_batch)
+            ws = self._workspace(hi - lo, want_grad)
+            chunk = np.ascontiguousarray(thetas[lo:hi])
+            call("gpb_gp_eval", self.kind, chunk.ctypes.data_as(_lib.dp), hi - lo, D.ptr(self.dx),
+                 D.ptr(self.dy), self.n, int(want_grad), D.ptr(ws), ws.numel(), res[lo:].data_ptr(),
+                 D.stream_ptr())
+        return res
+
+    def eval(self, thetas, want_grad=True):
+        """(log_lh[B], dloglh[B, n_theta], info[B]) as numpy arrays."""
+        r = D.to_host(self.eval_device(thetas, want_grad))
+        return r[:, 0].copy(), r[:, 1:1 + self.nth].copy(), r[:, 7].astype(np.int64)

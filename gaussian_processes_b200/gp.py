@@ -1,0 +1,361 @@
+"""``GP``: the reference's Gaussian-process object (reference: gp/gp.py:44-700) with the
+same constructor, properties, methods, memo/invalidate semantics, copy/pickle state and
+error behaviour -- computed by the sm_100a CUDA path instead of numpy/scipy/Cython.
+
+Residency: matrix-valued intermediates (Kxx, its Cholesky factor, the triangular
+inverse, K^-1) live on the device in ``self._dev`` and are only copied to the host when
+the user reads a matrix-valued property.  ``gp.log_lh`` / ``gp.dloglh_dtheta`` move
+``n_theta + 1`` doubles over PCIe, never an N x N array.  ``_memoized`` holds exactly
+what the reference's holds (the values the properties returned), so its keys, its
+``del`` semantics and its place in the pickled state are unchanged
+(gp/tests/test_gp.py:245-279).
+"""
+import copy as _copy
+
+import numpy as np
+
+from . import engine as _engine
+
+__all__ = ["GP"]
+
+DTYPE = np.float64
+EPS = np.finfo(DTYPE).eps
+MIN = np.log(np.exp2(DTYPE(np.finfo(DTYPE).minexp + 4)))      # gp.py:17
+
+
+class memoprop(object):
+    """Property whose value is computed once and kept in ``obj._memoized[name]``;
+    ``del obj.name`` forgets it (semantics of gp.py:20-41)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.name = fn.__name__
+        self.__doc__ = fn.__doc__
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        cache = obj._memoized
+        if self.name not in cache:
+            cache[self.name] = self.fn(obj)
+        return cache[self.name]
+
+    def __set__(self, obj, value):
+        raise AttributeError("can't set attribute")
+
+    def __delete__(self, obj):
+        del obj._memoized[self.name]
+
+
+class GP(object):
+    r"""
+    Gaussian Process object.
+
+    Parameters
+    ----------
+    K : :class:`~gaussian_processes_b200.kernels.Kernel`
+        Kernel object
+    x : numpy.ndarray
+        :math:`n` array of input locations
+    y : numpy.ndarray
+        :math:`n` array of input observations
+    s : number (default=0)
+        Standard deviation of observation noise
+    """
+
+    _STATE = ("K", "_x", "_y", "_s", "_memoized")
+
+    def __init__(self, K, x, y, s=0):
+        self.K = K
+        self._x = None
+        self._y = None
+        self._s = None
+        self._memoized = {}
+        self._dev = None
+        self.x = x
+        self.y = y
+        self.s = s
+
+    # ------------------------------------------------------------------ state (gp.py:78-127)
+    def __getstate__(self):
+        return dict((k, getattr(self, k)) for k in self._STATE)
+
+    def __setstate__(self, state):
+        for k in self._STATE:
+            setattr(self, k, state[k])
+        self._dev = None
+
+    def __copy__(self):
+        new = type(self).__new__(type(self))
+        new.__setstate__(self.__getstate__())
+        return new
+
+    def __deepcopy__(self, memo):
+        new = type(self).__new__(type(self))
+        new.__setstate__(_copy.deepcopy(self.__getstate__(), memo))
+        return new
+
+    def copy(self, deep=True):
+        """Deep (default) or shallow copy of the GP."""
+        return _copy.deepcopy(self) if deep else _copy.copy(self)
+
+    def _reset(self):
+        self._memoized = {}
+        self._dev = None
+
+    # ------------------------------------------------------------------ inputs (gp.py:129-240)
+    @property
+    def x(self):
+        r"""Vector of input locations (read-only array)."""
+        return self._x
+
+    @x.setter
+    def x(self, val):
+        if np.any(val != self._x):
+            self._reset()
+            self._x = np.array(val, copy=True, dtype=DTYPE)
+            self._x.flags.writeable = False
+
+    @property
+    def y(self):
+        r"""Vector of input observations (read-only array)."""
+        return self._y
+
+    @y.setter
+    def y(self, val):
+        if np.any(val != self._y):
+            self._reset()
+            self._y = np.array(val, copy=True, dtype=DTYPE)
+            self._y.flags.writeable = False
+            if self._y.shape != self._x.shape:
+                raise ValueError("invalid shape for y: %s" % str(self._y.shape))
+
+    @property
+    def s(self):
+        r"""Standard deviation of the observation noise (numpy.float64)."""
+        return self._s
+
+    @s.setter
+    def s(self, val):
+        if val < 0:
+            raise ValueError("invalid value for s: %s" % val)
+        if val != self._s:
+            self._reset()
+            self._s = DTYPE(val)
+
+    @property
+    def params(self):
+        r"""Kernel parameters followed by the noise parameter :math:`s`."""
+        kp = self.K.params
+        out = np.empty(kp.size + 1)
+        out[:-1] = kp
+        out[-1] = self._s
+        return out
+
+    @params.setter
+    def params(self, val):
+        if np.any(self.params != val):
+            self._reset()
+            self.K.params = val[:-1]
+            self.s = val[-1]
+
+    def get_param(self, name):
+        return self.s if name == "s" else getattr(self.K, name)
+
+    def set_param(self, name, val):
+        if name == "s":
+            self.s = val
+        elif getattr(self.K, name) != val:
+            self._reset()
+            self.K.set_param(name, val)
+
+    # ------------------------------------------------------------------ device state
+    def _engine(self):
+        """Device-side twin of the current (K, x, y, s); dropped by every setter."""
+        kp = tuple(float(v) for v in self.K.params)
+        key = (type(self.K).KIND, kp, float(self._s))
+        if self._dev is None or self._dev[0] != key:
+            self._dev = (key, _engine.Engine(key[0], kp, key[2], self._x, self._y))
+        return self._dev[1]
+
+    def _n_theta(self):
+        return self.K.params.size + 1
+
+    def _nan(self, *shape):
+        out = np.empty(shape)
+        out.fill(np.nan)
+        return out
+
+    # ------------------------------------------------------------------ matrices (gp.py:242-335)
+    @memoprop
+    def Kxx(self):
+        r"""Kernel covariance matrix :math:`K(x_i, x_j) + s^2\delta_{ij}` (:math:`n\times n`)."""
+        e = self._engine()
+        from . import device as D
+        return D.to_host(e.Kxx()[:e.n, :e.n]).copy()
+
+    @memoprop
+    def Kxx_J(self):
+        x = self._x
+        return self.K.jacobian(x, x)
+
+    @memoprop
+    def Kxx_H(self):
+        x = self._x
+        return self.K.hessian(x, x)
+
+    @memoprop
+    def Lxx(self):
+        r"""Lower Cholesky factor of ``Kxx``; raises ``numpy.linalg.LinAlgError`` when
+        ``Kxx`` is not positive definite."""
+        return self._engine().Lxx_host()
+
+    @memoprop
+    def inv_Kxx(self):
+        r"""Inverse kernel covariance matrix :math:`\mathbf{K}_{xx}^{-1}` (from the Cholesky factor)."""
+        e = self._engine()
+        e.require_pd()
+        from . import device as D
+        return D.to_host(e.Ki()[:e.n, :e.n]).copy()
+
+    @memoprop
+    def inv_Kxx_y(self):
+        r""":math:`\mathbf{K}_{xx}^{-1}\mathbf{y}` by Cholesky solves."""
+        e = self._engine()
+        from . import device as D
+        return D.to_host(e.alpha()[:e.n]).copy()
+
+    # ------------------------------------------------------------------ likelihood (gp.py:337-502)
+    @memoprop
+    def log_lh(self):
+        r"""Marginal log likelihood (Eq. 5.8 of Rasmussen & Williams); ``-inf`` when the
+        Cholesky fails or :math:`\log|\mathbf{K}_{xx}|` is below ``MIN``."""
+        e = self._engine()
+        try:
+            e.require_pd()
+        except np.linalg.LinAlgError:
+            return -np.inf
+        return DTYPE(e.loglh3()[0])
+
+    @memoprop
+    def lh(self):
+        r"""Marginal likelihood; integer 0 when ``log_lh`` is below ``MIN``."""
+        llh = self.log_lh
+        if llh < MIN:
+            return 0
+        return np.exp(self.log_lh)
+
+    def _grad_bracket(self):
+        """(y^T Ki dK_i Ki y, tr(Ki dK_i)) per parameter, or None when Kxx is not PD."""
+        e = self._engine()
+        try:
+            e.require_pd()
+        except np.linalg.LinAlgError:
+            return None
+        return e.grad_terms()
+
+    @memoprop
+    def dloglh_dtheta(self):
+        r"""Derivative of the marginal log likelihood w.r.t. ``params`` (Eq. 5.9 of R&W)."""
+        terms = self._grad_bracket()
+        if terms is None:
+            return self._nan(self._n_theta())
+        t0, t1 = terms
+        return 0.5 * t0 + -0.5 * t1                                  # gp_c.pyx:47-49
+
+    @memoprop
+    def dlh_dtheta(self):
+        r"""Derivative of the marginal likelihood w.r.t. ``params``."""
+        terms = self._grad_bracket()
+        if terms is None:
+            return self._nan(self._n_theta())
+        t0, t1 = terms
+        return 0.5 * self.lh * (t0 - t1)                             # gp_c.pyx:65-67
+
+    def _d2lh(self, lh, dlh):
+        e = self._engine()
+        t0, t1 = e.grad_terms()
+        G, Q, TP, TH = e.d2_terms()
+        nth = self._n_theta()
+        out = np.empty((nth, nth))
+        for i in range(nth):
+            r_i = t0[i] - t1[i]                                      # gp_c.pyx:92-93
+            for j in range(nth):
+                t1a = -G[i, j]                                       # y^T dKi_j dK_i Kiy
+                t1c = -G[j, i]                                       # Kiy^T dK_i dKi_j y
+                tr = -TP[i, j] + TH[i, j]                            # trace(dKi_j dK_i + Ki d2k)
+                out[i, j] = 0.5 * (dlh[j] * r_i + lh * (t1a + Q[i, j] + t1c - tr))
+        return out
+
+    @memoprop
+    def d2lh_dtheta2(self):
+        r"""Second derivative (Hessian) of the marginal likelihood w.r.t. ``params``."""
+        nth = self._n_theta()
+        if self._grad_bracket() is None:
+            return self._nan(nth, nth)
+        return self._d2lh(self.lh, self.dlh_dtheta)
+
+    def d2loglh_normalised(self):
+        r"""``gp_c.d2lh_dtheta2`` evaluated with ``lh = 1`` and ``dlh = dloglh_dtheta``: the
+        likelihood-normalised second derivative :math:`(\partial^2 p/\partial\theta^2)/p`, usable at
+        sizes where ``lh`` underflows to 0 (additive API)."""
+        if self._grad_bracket() is None:
+            nth = self._n_theta()
+            return self._nan(nth, nth)
+        return self._d2lh(1.0, self.dloglh_dtheta)
+
+    # ------------------------------------------------------------------ posterior (gp.py:504-662)
+    def Kxoxo(self, xo):
+        r"""Kernel covariance matrix of new sample locations (:math:`m\times m`)."""
+        return self.K(xo, xo)
+
+    def Kxxo(self, xo):
+        r"""Kernel covariance between given and new locations (:math:`n\times m`)."""
+        return self.K(self._x, xo)
+
+    def Kxox(self, xo):
+        r"""Kernel covariance between new and given locations (:math:`m\times n`)."""
+        return self.K(xo, self._x)
+
+    def mean(self, xo):
+        r"""Predictive mean :math:`K(\mathbf{x^*},\mathbf{x})\mathbf{K}_{xx}^{-1}\mathbf{y}` (Eq. 2.23 of R&W)."""
+        return self._engine().mean(np.asarray(xo, dtype=DTYPE))
+
+    def cov(self, xo):
+        r"""Predictive covariance (Eq. 2.24 of R&W), :math:`m\times m`."""
+        return self._engine().cov(np.asarray(xo, dtype=DTYPE))
+
+    def dm_dtheta(self, xo):
+        r"""Derivative of the predictive mean w.r.t. ``params``: :math:`n_\theta\times m`."""
+        return self._engine().dm(np.asarray(xo, dtype=DTYPE))
+
+    def plot(self, ax=None, xlim=None, color="k", markercolor="r"):
+        """Plot the predictive mean +/- one standard deviation (needs matplotlib)."""
+        import matplotlib.pyplot as plt
+        x, y = self._x, self._y
+        if ax is None:
+            ax = plt.gca()
+        if xlim is None:
+            xlim = (x.min(), x.max())
+        X = np.linspace(xlim[0], xlim[1], 1000)
+        mean = self.mean(X)
+        std = np.sqrt(np.diag(self.cov(X)))
+        ax.fill_between(X, mean - std, mean + std, color=color, alpha=0.3)
+        ax.plot(X, mean, lw=2, color=color)
+        ax.plot(x, y, "o", ms=5, color=markercolor)
+        ax.set_xlim(*xlim)
+
+    # ------------------------------------------------------------------ batched search (additive)
+    def batch_eval(self, thetas, grad=True):
+        """log_lh (and dloglh_dtheta) for many parameter vectors on this GP's (x, y).
+
+        thetas : [B, n_theta] rows ordered like ``params``.  Returns ``(log_lh[B],
+        dloglh[B, n_theta])``; a candidate whose Kxx is not positive definite gets
+        ``-inf`` / NaN exactly like the scalar properties."""
+        from .mlii import batch_eval
+        return batch_eval(self, thetas, grad=grad)
+
+    def fit_MLII(self, candidates, **kw):
+        """Type-II maximum likelihood by batched multi-restart search (see mlii.fit_MLII)."""
+        from .mlii import fit_MLII
+        return fit_MLII(self, candidates, **kw)

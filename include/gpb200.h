@@ -1,0 +1,186 @@
+/*
+ * gpb200.h -- C ABI of libgpb200.so: the B200 (sm_100a) GP-regression hot path.
+ *
+ * Drop-in boundary for jhamrick/gaussian_processes v1.0.5.  The reference's native
+ * layer is three Cython modules (gp/ext/gaussian_c.pyx, periodic_c.pyx, gp_c.pyx)
+ * plus the LAPACK calls gp/gp.py makes through scipy/numpy; every entry point
+ * below names the reference interface it replaces (file:line under the reference
+ * tree).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - all matrices are row-major (C order) fp64, like the reference's numpy arrays;
+ *   - "*_host" / "gpb_gaussian_*" / "gpb_periodic_*" entry points take HOST pointers and
+ *     do their own host<->device copies (what a ctypes/cffi binding of the
+ *     reference's Cython signatures would call);
+ *   - all other entry points take DEVICE pointers and a cudaStream_t (as void*),
+ *     launch asynchronously and never retain pointers;
+ *   - device matrices used by the factorisation are padded to a multiple of 128
+ *     (GPB_NB) with an identity pad, see DESIGN.md "Data layout";
+ *   - return value: 0 ok, <0 error (gpb_last_error() has the text).  Cholesky
+ *     failure is NOT an error code: it is reported through the device `info` word
+ *     (LAPACK convention: index+1 of the first non-positive pivot), which the Python
+ *     layer turns into numpy.linalg.LinAlgError exactly where gp/gp.py:294 raises.
+ *   - not thread-safe per handle-less call: one host thread per stream.
+ */
+#ifndef GPB200_H
+#define GPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_KIND_GAUSSIAN 0   /* gp/kernels/gaussian.py:14, params (h, w)    */
+#define GPB_KIND_PERIODIC 1   /* gp/kernels/periodic.py:14, params (h, w, p) */
+#define GPB_BLOCK 128         /* padding / blocking unit of the device matrices */
+
+/* ---- library ------------------------------------------------------------ */
+int gpb_version(void);
+const char* gpb_last_error(void);
+/* MIN = log(exp2(minexp+4)): gaussian_c.pyx:15, gp_c.pyx:14, gp.py:17 */
+double gpb_min_log(void);
+
+/* ---- kernel-matrix builders, device pointers -------------------------------
+ * Slice ids (the order jacobian()/hessian() stack them in the reference):
+ *   Gaussian: 0 K | 1 dK_dh 2 dK_dw | 3 hh 4 hw 5 wh 6 ww
+ *   Periodic: 0 K | 1 dh 2 dw 3 dp | 4 hh 5 hw 6 hp 7 wh 8 ww 9 wp 10 ph 11 pw 12 pp
+ * Every slice selected in `slice_mask` is written, in slice-id order, to
+ * out + q * slice_stride (q = rank among the selected slices) with row stride ld.
+ * rows/cols >= n1/n2: the pad region is 0, or the identity for slice 0 when
+ * pad_identity.  add_diag adds s^2 on the index diagonal of slice 0 (gp.py:265).
+ * theta = (h, w[, p]) on the HOST.
+ * Replaces gaussian_c.K, jacobian, hessian, dK_dX, d2K_dXdY (gaussian_c.pyx:18-164) and
+ * periodic_c.* (periodic_c.pyx:18-235) in one fused pass.                        */
+int gpb_kernel_build(int kind, const double* theta, double s, const double* x1, int64_t n1,
+                     const double* x2, int64_t n2, int64_t rows, int64_t cols,
+                     unsigned slice_mask, double* out, int64_t ld, int64_t slice_stride,
+                     int add_diag, int pad_identity, void* stream);
+
+/* out[g][r] = sum_p coef[p] * sum_c slice[p](x1[r], x2[c]) * vec[p][c]   (never
+ * materialises the n1 x n2 kernel matrix).  Serves GP.mean (gp.py:597), the
+ * mat-vecs of gp_c.dm_dtheta (gp_c.pyx:122-131) and dK_i * alpha.  npairs <= 8, nout <= 4. */
+int gpb_kernel_matvec(int kind, const double* theta, const double* x1, int64_t n1,
+                      const double* x2, int64_t n2, int npairs, const int* slice,
+                      const int* outidx, const double* coef, const double* const* vec,
+                      int nout, double* const* out, void* stream);
+
+/* ---- factorisation and solves, device pointers (n multiple of 128) ---------- */
+/* In-place lower Cholesky of the batch of n x n matrices A (strict upper part of the
+ * diagonal blocks zeroed, off-diagonal upper tiles untouched -- see gpb_tril).  Also
+ * writes the inverted 128x128 diagonal blocks into W (lower) and, if V != NULL, their
+ * transposes into V.  info[b] = 0 or first failing column + 1.
+ * Replaces scipy.linalg.cholesky(lower=True) at gp/gp.py:294.                       */
+int gpb_potrf(double* A, int64_t n, int64_t ld, int64_t stride_a, int batch, double* W,
+              int64_t ldw, int64_t stride_w, double* V, int64_t ldv, int64_t stride_v,
+              int* info, void* stream);
+/* alpha = (L L^T)^-1 y by substitution; z = scratch [batch][n]; flags = int scratch
+ * [2*batch*n/128 + 2].  Replaces scipy.linalg.cho_solve at gp/gp.py:332-334.          */
+int gpb_potrs(const double* L, const double* W, int64_t n, int64_t ld, int64_t ldw,
+              int64_t stride_l, int64_t stride_w, int batch, const double* y, int64_t stride_y,
+              double* z, double* alpha, int64_t stride_vec, int* flags, void* stream);
+/* W = L^-1 (lower), V = W^T (upper) completed from the diagonal blocks left by
+ * gpb_potrf; T = n x n scratch.  Replaces np.linalg.inv(Lxx) at gp/gp.py:311.         */
+int gpb_trtri(const double* L, int64_t n, int64_t ld, int64_t stride_l, int batch, double* W,
+              int64_t ldw, int64_t stride_w, double* V, int64_t ldv, int64_t stride_v,
+              double* T, int64_t ldt, int64_t stride_t, void* stream);
+/* Ki = V V^T = inv(L)^T inv(L), full symmetric.  Replaces np.dot at gp/gp.py:312.     */
+int gpb_lauum(const double* V, int64_t n, int64_t ldv, int64_t stride_v, int batch, double* Ki,
+              int64_t ldk, int64_t stride_k, void* stream);
+/* zero the strict upper triangle (what scipy returns for Lxx).                          */
+int gpb_tril(double* A, int64_t n, int64_t ld, void* stream);
+int gpb_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows,
+               int64_t cols, void* stream);
+
+/* C = beta*C + alpha * A * B^T on FP64 tensor cores (DMMA); M, N multiples of 128, K of 16.
+ * a_tri/b_tri: 0 dense, 1 lower (A[i][k] = 0 for k > i), 2 upper (k < i): zero tiles
+ * are skipped.  lower_only: only tiles on/below the diagonal, mirrored into Ct.
+ * The products of GP.cov (gp.py:625) and gp_c.d2lh_dtheta2 (gp_c.pyx:81-111) run here. */
+int gpb_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                int64_t ldc, double* Ct, int64_t ldct, int64_t M, int64_t N, int64_t K,
+                double alpha, double beta, int a_tri, int b_tri, int lower_only, void* stream);
+
+/* ---- reductions, device pointers --------------------------------------------- */
+/* out3 = {log_lh, logdet, y.alpha}; log_lh = -inf if info != 0 or logdet < MIN.
+ * logdet = 2 sum log L_ii.  Replaces gp_c.log_lh (gp_c.pyx:17-31).                     */
+int gpb_loglh(const double* L, int64_t n_valid, int64_t ld, const double* y,
+              const double* alpha, const int* info, double* out3, void* stream);
+/* For each requested slice S_q (q < nslices <= 6; any jacobian/hessian slice id):
+ *   out16[q] = a^T S_q a,  out16[6+q] = sum(Ki o S_q);  out16[12] = tr Ki, out16[13] = a.a.
+ * S_q is regenerated from x on the fly (one pass over Ki is the only HBM traffic).
+ * partial = scratch [gpb_grad_partial_doubles(n)].  The O(N^2) core of
+ * gp_c.dloglh_dtheta / dlh_dtheta (gp_c.pyx:34-67) and of the trace and quadratic-form
+ * terms of gp_c.d2lh_dtheta2 (gp_c.pyx:104-110).                                        */
+int gpb_slice_reduce(int kind, const double* theta, const double* x, int64_t n, const double* Ki,
+                     int64_t ldk, const double* alpha, int nslices, const int* slices,
+                     double* partial, double* out16, void* stream);
+int64_t gpb_grad_partial_doubles(int64_t n);
+/* y = alpha * A x + beta * y                                                          */
+int gpb_gemv(const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y,
+             double alpha, double beta, void* stream);
+/* *out = sum_ab A[a,b] B[b,a] = trace(A B)   (np.trace(np.dot(..)) in gp_c.pyx:49,110)  */
+int gpb_trace_prod(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t n,
+                   double* partial, double* out, void* stream);
+/* *out = u^T M v                                                                      */
+int gpb_quadform(const double* u, const double* M, int64_t ldm, const double* v, int64_t n,
+                 double* partial, double* out, void* stream);
+
+/* ---- fused evaluator: log_lh + dloglh_dtheta for a batch of hyperparameter
+ * candidates on fixed (x, y) -- the unit of the headline metric and of fit_MLII.
+ * thetas: HOST [batch][n_theta] rows (kernel params..., s).  x, y: DEVICE [n].
+ * result: DEVICE [batch][8] = {log_lh, dloglh[0..3] (unused = 0), logdet, y.alpha, info}.
+ * dloglh is NaN and log_lh -inf for a candidate whose Cholesky fails (gp.py:362-365,
+ * 424-428).  want_grad = 0 skips inverse + gradient.
+ * Replaces, per candidate, GP.Kxx/Lxx/inv_Kxx_y/inv_Kxx/log_lh/dloglh_dtheta
+ * (gp/gp.py:242-433).                                                                 */
+size_t gpb_eval_workspace_bytes(int64_t n, int batch, int want_grad);
+int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, const double* y,
+                int64_t n, int want_grad, void* workspace, size_t workspace_bytes,
+                double* result, void* stream);
+/* same with HOST x, y, result: uploads, evaluates, downloads, synchronises.            */
+int gpb_gp_eval_host(int kind, const double* thetas, int batch, const double* x, const double* y,
+                     int64_t n, int want_grad, double* result);
+
+/* ---- host-buffer drop-ins for the reference's Cython signatures ----------------
+ * f(out, x1, x2, h, w[, p]) with caller-allocated C-contiguous out, exactly the
+ * arguments of gaussian_c.pyx:18,39,44,51,72,95,116,139,143 and
+ * periodic_c.pyx:18,33,39,53,68,83,99,...,223 (sizes made explicit).                   */
+int gpb_kernel_slices_host(int kind, unsigned slice_mask, double* out, const double* x1,
+                           int64_t n1, const double* x2, int64_t n2, const double* theta);
+int gpb_gaussian_K(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_jacobian(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_hessian(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_dK_dh(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_dK_dw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_d2K_dhdh(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_d2K_dhdw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_d2K_dwdh(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_gaussian_d2K_dwdw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w);
+int gpb_periodic_K(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_jacobian(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_hessian(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_dK_dh(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_dK_dw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_dK_dp(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dhdh(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dhdw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dhdp(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dwdh(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dwdw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dwdp(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dpdh(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dpdw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+int gpb_periodic_d2K_dpdp(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
+
+/* ---- measurement helpers ----------------------------------------------------------
+ * FP64 tensor (DMMA.8x8x4) and FP64 FMA issue-rate microbenchmarks: the roofline
+ * denominator for the factorisation (MEASURED_PEAKS.json has no fp64 figure).          */
+int gpb_microbench_fp64(int use_dmma, int iters, double* tflops, double* ms);
+/* number of kernel launches issued by this library since load (bench.py gpu_launches) */
+int64_t gpb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H */
