@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json on B200:
+log_lh + dloglh_dtheta evaluations / second at N = 4096, fp64 (config C2).
+
+One *step* = one pass of the hot path over one batch of B hyperparameter candidates on a
+fixed synthetic 1-D data set (x = sort U(-2pi, 2pi), y = sin x + 0.1 N(0,1), seed 0; SURVEY
+8d): Kxx build -> blocked Cholesky -> solves -> log_lh -> inverse -> fused gradient, for
+every candidate (what one iteration of a multi-restart MLII search costs).  Every step uses
+different candidates, so nothing can be reused between steps.
+
+  python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W    (the reference's CPU path)
+
+`value`  : whole-job evals/s with x, y resident in HBM, timed with CUDA events on the launch
+           stream, max over ranks.
+`e2e`    : the same metric through the public Python API (GP.batch_eval) with HOST x, y,
+           thetas and results every step (pinned staging, H2D + D2H inside the timed region).
+`roofline`: the DMMA GEMM kernel (all O(N^3) work): algorithmic flops / its event-timed
+           duration, against the FP64 DMMA issue rate measured live on the same GPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DEFAULT = 4096
+BASE_THETA = np.array([1.0, 0.5, 1.0])      # Gaussian(h=1, w=0.5), s=1
+
+
+def synth_xy(n, seed=0):
+    rng = np.random.RandomState(seed)
+    x = np.sort(rng.uniform(-2 * np.pi, 2 * np.pi, n))
+    y = np.sin(x) + 0.1 * rng.randn(n)
+    return x, y
+
+
+def candidates(step, rank, batch):
+    """Deterministic, step- and rank-dependent candidates around the C2 parameters
+    (h in [0.9,1.1], w in [0.45,0.55], s in [0.95,1.05]: logdet stays above MIN)."""
+    rng = np.random.RandomState(1000003 * rank + step)
+    return BASE_THETA * (1.0 + 0.1 * rng.uniform(-1, 1, (batch, 3))) * [1.0, 1.0, 0.5] + [0, 0, 0.5]
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        busy = [c for c, p in zip(sm, power) if p > 300] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def load_oracle():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gp_oracle", os.path.join(ROOT, "oracle", "gp_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["gp_oracle"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_eval_once(oracle, impl, x, y, theta):
+    """Cold-cache GP.log_lh + GP.dloglh_dtheta the way gp/gp.py computes them (fresh object)."""
+    g = oracle.OracleGP(oracle.GAUSSIAN, theta[:2], x, y, theta[2], impl)
+    return float(g.log_lh), g.dloglh_dtheta
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores:
+    oracle/_ref (its compiled Cython) + the scipy/numpy calls gp/gp.py makes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    oracle = load_oracle()
+    impl = "ref" if oracle.have_ref() else "c"
+    x, y = synth_xy(args.n, 0)
+    th = candidates(0, 0, max(args.steps + args.warmup, 1))
+    for w in range(args.warmup):
+        cpu_eval_once(oracle, impl, x, y, th[w])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_eval_once(oracle, impl, x, y, th[args.warmup + k])
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    cores = blas_threads()
+    sample = "1 candidate (one cold-cache log_lh + dloglh_dtheta at N=%d) per step" % args.n
+    line = {
+        "impl": "reference", "metric": "log_lh+dloglh_dtheta evals/sec at N=%d fp64" % args.n,
+        "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: GaussianKernel 1-D GP, N=%d, log_lh + dloglh_dtheta per candidate" % args.n,
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores,
+                         "kind": "reference" if impl == "ref" else "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import gaussian_processes_b200 as gpb
+    from gaussian_processes_b200 import _lib, engine
+    import ctypes
+
+    n, B, K, W = args.n, args.batch, args.steps, args.warmup
+    x, y = synth_xy(n, 0)
+    ev = engine.BatchEvaluator(engine.GAUSSIAN, x, y, max_batch=B)
+    nth = 3
+    table = torch.empty(world * B, 8, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step(k):
+        res = ev.eval_device(candidates(k, rank, B), want_grad=True)
+        if world > 1:       # the path's one exchange: gather per-candidate rows, argmax everywhere
+            dist.all_gather_into_tensor(table, res)
+            return torch.argmax(torch.nan_to_num(table[:, 0], nan=-float("inf")))
+        return res
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(W, 3)):
+        step(k)
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib.gpb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for k in range(K):
+        step(100 + k)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.lib.gpb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end through the public API, host buffers every step -------------------
+    gp = gpb.GP(gpb.GaussianKernel(1.0, 0.5), x, y, s=1.0)
+    shifts = [x + 1e-9 * (k + 1) for k in range(K + 2)]
+    for k in range(2):
+        gp.x = shifts[k]
+        gp.batch_eval(candidates(50 + k, rank, B))
+    sync()
+    t0 = time.perf_counter()
+    for k in range(K):
+        gp.x = shifts[2 + k]            # new host arrays: pinned staging + H2D inside the timed region
+        gp.y = y + 0.0
+        llh, grad = gp.batch_eval(candidates(200 + k, rank, B))      # D2H of the [B, 8] result
+    sync()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * B * K / float(te.item())
+
+    # ---- roofline of the dominant kernel (DMMA GEMM), event-timed per launch --------------
+    roof = None
+    cpu = None
+    if rank == 0:
+        tf, pms = ctypes.c_double(), ctypes.c_double()
+        _lib.call("gpb_microbench_fp64", 1, 20000, ctypes.byref(tf), ctypes.byref(pms))
+        peak = tf.value
+        _lib.lib.gpb_profile_enable.argtypes = [ctypes.c_int]
+        _lib.lib.gpb_profile_enable.restype = None
+        _lib.lib.gpb_profile_read.argtypes = [ctypes.c_int, _lib.dp, ctypes.POINTER(ctypes.c_int64)]
+        _lib.lib.gpb_profile_enable(1)
+        psteps = 2
+        for k in range(psteps):
+            ev.eval_device(candidates(300 + k, rank, B), want_grad=True)
+        torch.cuda.synchronize()
+        classes = {}
+        for cid, nm in enumerate(["gemm_nt(DMMA)", "potrf_diag", "build+matvec", "trsv", "reduce", "misc"]):
+            m, c = ctypes.c_double(), ctypes.c_int64()
+            _lib.lib.gpb_profile_read(cid, ctypes.byref(m), ctypes.byref(c))
+            classes[nm] = {"ms_per_step": m.value / psteps, "launches_per_step": c.value / psteps}
+        _lib.lib.gpb_profile_enable(0)
+        gemm_ms = classes["gemm_nt(DMMA)"]["ms_per_step"]
+        gemm_launches = max(classes["gemm_nt(DMMA)"]["launches_per_step"], 1)
+        flops_step = B * float(n) ** 3            # N^3/3 potrf + 2N^3/3 inverse per eval
+        achieved = flops_step / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA.8x8x4)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "algorithmic_flops_per_launch": flops_step / gemm_launches,
+                "avg_launch_ms": gemm_ms / gemm_launches, "launches_per_step": gemm_launches,
+                "peak_source": "measured live: gpb_microbench_fp64 (DMMA.8x8x4 issue rate, 148x8 CTAs); "
+                               "MEASURED_PEAKS.json has no fp64 figure",
+                "whole_step_frac": flops_step / (ms / K * 1e-3) / 1e12 / peak,
+                "kernel_classes": classes}
+        # ---- CPU baseline: the reference's path on this box's host cores (bounded sample) ------
+        if world == 1 and not args.no_cpu_baseline:
+            oracle = load_oracle()
+            impl = "ref" if oracle.have_ref() else "c"
+            th = candidates(0, 0, 3)
+            cpu_eval_once(oracle, impl, x, y, th[0])
+            t0 = time.perf_counter()
+            ns = 2
+            for k in range(ns):
+                cl, cg = cpu_eval_once(oracle, impl, x, y, th[1 + k])
+            cdt = time.perf_counter() - t0
+            cpu = {"value": ns / cdt, "unit": "evals/s", "cores": blas_threads(),
+                   "kind": "reference" if impl == "ref" else "port",
+                   "sample": "%d of the %d candidates of one step (N=%d), after 1 warm-up eval" % (ns, B, n)}
+            # the sample doubles as a parity spot-check of the timed path
+            chk = ev.eval(th[1 + ns - 1:1 + ns], want_grad=True)
+            cpu["parity_rel_err_log_lh"] = abs(chk[0][0] - cl) / abs(cl)
+            cpu["parity_rel_err_grad"] = float(np.max(np.abs(chk[1][0] - cg)) / np.max(np.abs(cg)))
+
+    if rank == 0:
+        line = {
+            "metric": "log_lh+dloglh_dtheta evals/sec at N=%d fp64" % n,
+            "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: GaussianKernel 1-D GP, N=%d, Kxx build + Cholesky + log_lh + dloglh_dtheta "
+                                   "for a batch of %d hyperparameter candidates per GPU per step" % (n, B),
+                       "batch_per_gpu": B, "n": n, "theta": "h,w,s around (1, 0.5, 1); new candidates every step",
+                       "l2": "working set %.1f GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)"
+                             % (4 * B * n * n * 8 / 1e9),
+                       "parallelism": "candidates sharded over %d GPU(s), NCCL all-gather of [B,8] rows + argmax" % world},
+            "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 2 * n * 8 + B * nth * 8,
+                    "d2h_bytes_per_step": B * 8 * 8},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="candidates per GPU per step")
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

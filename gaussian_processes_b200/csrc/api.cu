@@ -23,6 +23,42 @@ int gpb_check_cuda(cudaError_t e, const char* what) {
     return GPB_ERR_CUDA;
 }
 
+// ---- per-class timing -------------------------------------------------------------
+int g_gpb_profile = 0;
+struct ProfPair { cudaEvent_t a, b; int cls; };
+static std::vector<ProfPair> g_prof_pairs;
+static std::vector<cudaEvent_t> g_prof_open[GPB_KC_COUNT];
+static double g_prof_ms[GPB_KC_COUNT];
+static long long g_prof_n[GPB_KC_COUNT];
+
+void gpb_prof_begin(int cls, cudaStream_t st) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof_open[cls].push_back(e);
+}
+void gpb_prof_end(int cls, cudaStream_t st) {
+    if (g_prof_open[cls].empty()) return;
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) != cudaSuccess) return;
+    cudaEventRecord(b, st);
+    ProfPair p = {g_prof_open[cls].back(), b, cls};
+    g_prof_open[cls].pop_back();
+    g_prof_pairs.push_back(p);
+}
+static void prof_collect() {
+    for (auto& p : g_prof_pairs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_prof_ms[p.cls] += ms;
+            g_prof_n[p.cls] += 1;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_prof_pairs.clear();
+}
+
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline long long roundup(long long n, long long m) { return (n + m - 1) / m * m; }
 
@@ -102,6 +138,19 @@ int gpb_version(void) { return 100; }
 const char* gpb_last_error(void) { return g_err; }
 double gpb_min_log(void) { return GPB_MIN_LOG; }
 int64_t gpb_launch_count(void) { return g_gpb_launches; }
+
+void gpb_profile_enable(int on) {
+    prof_collect();
+    g_gpb_profile = on;
+    if (on) for (int c = 0; c < GPB_KC_COUNT; c++) { g_prof_ms[c] = 0.0; g_prof_n[c] = 0; }
+}
+int gpb_profile_read(int cls, double* ms, int64_t* launches) {
+    GPB_REQUIRE(cls >= 0 && cls < GPB_KC_COUNT, "bad kernel class");
+    prof_collect();
+    *ms = g_prof_ms[cls];
+    *launches = g_prof_n[cls];
+    return GPB_OK;
+}
 
 int gpb_kernel_build(int kind, const double* theta, double s, const double* x1, int64_t n1,
                      const double* x2, int64_t n2, int64_t rows, int64_t cols, unsigned slice_mask,

@@ -120,6 +120,7 @@ int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, c
     dim3 block(32, 8);
     dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 31) / 32), (unsigned)batch);
     GPB_REQUIRE(grid.y <= 65535 && batch <= 65535, "extent too large for the launch grid");
+    GpbProfScope prof(GPB_KC_BUILD, st);
     if (kind == GPB_GAUSSIAN) {
         if (vec) build_kernel<GPB_GAUSSIAN, true><<<grid, block, 0, st>>>(a);
         else build_kernel<GPB_GAUSSIAN, false><<<grid, block, 0, st>>>(a);
@@ -214,6 +215,7 @@ int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int b
     long long nb = (n1 + 7) / 8;
     if (nb > 148 * 16) nb = 148 * 16;
     dim3 grid((unsigned)nb, 1, (unsigned)batch);
+    GpbProfScope prof(GPB_KC_BUILD, st);
     if (kind == GPB_GAUSSIAN) fused_matvec_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
     else fused_matvec_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
     GPB_LAUNCH_CHECK("fused_matvec_kernel");
@@ -336,6 +338,7 @@ int gpb_launch_grad_reduce(int kind, const KParams* P, const KParams* Pb, int ba
     }
     const int nb = gpb_grad_reduce_blocks(n);
     dim3 grid((unsigned)nb, 1, (unsigned)batch);
+    GpbProfScope prof(GPB_KC_REDUCE, st);
     if (kind == GPB_GAUSSIAN) grad_reduce_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
     else grad_reduce_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
     GPB_LAUNCH_CHECK("grad_reduce_kernel");

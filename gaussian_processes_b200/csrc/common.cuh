@@ -31,6 +31,22 @@ extern long long g_gpb_launches;   // kernels launched by this library (bench.py
         GPB_CUDA(cudaPeekAtLastError());                            \
     } while (0)
 
+// ---------------------------------------------------------------------------
+// optional per-kernel-class device timing (bench.py roofline): when enabled, every
+// launch of a class is bracketed by CUDA events on its own stream.
+// ---------------------------------------------------------------------------
+enum GpbKernelClass { GPB_KC_GEMM = 0, GPB_KC_DIAG = 1, GPB_KC_BUILD = 2, GPB_KC_SOLVE = 3,
+                      GPB_KC_REDUCE = 4, GPB_KC_MISC = 5, GPB_KC_COUNT = 6 };
+extern int g_gpb_profile;
+void gpb_prof_begin(int cls, cudaStream_t st);
+void gpb_prof_end(int cls, cudaStream_t st);
+struct GpbProfScope {
+    int cls;
+    cudaStream_t st;
+    GpbProfScope(int c, cudaStream_t s) : cls(c), st(s) { if (g_gpb_profile) gpb_prof_begin(cls, st); }
+    ~GpbProfScope() { if (g_gpb_profile) gpb_prof_end(cls, st); }
+};
+
 #define GPB_REQUIRE(cond, msg)                                      \
     do {                                                            \
         if (!(cond)) {                                              \

@@ -173,6 +173,7 @@ int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st) {
         grid = dim3((unsigned)tm, (unsigned)tn, (unsigned)(batch * p.nb1));
     }
     GPB_REQUIRE(batch >= 1 && (long long)batch * p.nb1 <= 65535, "bad batch");
+    GpbProfScope prof(GPB_KC_GEMM, st);
     gemm_nt_kernel<<<grid, 256, SMEM_BYTES, st>>>(p);
     GPB_LAUNCH_CHECK("gemm_nt_kernel");
     return GPB_OK;

@@ -395,6 +395,7 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     const int T = (int)(n / GPB_NB);
     for (int k = 0; k < T; k++) {
         const long long o = (long long)k * GPB_NB;
+        GpbProfScope prof(GPB_KC_DIAG, st);
         potrf_diag_kernel<<<batch, 256, DIAG_SMEM, st>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
                                                          V ? V + o * ldv + o : nullptr, ldv, sV, info,
                                                          (int)o);
@@ -494,6 +495,7 @@ int gpb_launch_potrs(const double* L, const double* W, long long n, long long ld
     const int T = (int)(n / GPB_NB);
     const size_t nfl = (size_t)2 * batch * T + 2;
     GPB_CUDA(cudaMemsetAsync(flags, 0, nfl * sizeof(int), st));
+    GpbProfScope prof(GPB_KC_SOLVE, st);
     int* fF = flags + 2;
     int* fB = fF + (size_t)batch * T;
     trsv_fwd_kernel<<<batch * T, 256, 0, st>>>(L, ld, sL, W, ldw, sW, y, sy, z, svec, T, fF, flags);
@@ -506,6 +508,7 @@ int gpb_launch_potrs(const double* L, const double* W, long long n, long long ld
 int gpb_launch_loglh(const double* L, long long n_valid, long long ld, long long sL, int batch,
                      const double* y, long long sy, const double* alpha, long long svec,
                      const int* info, double* out3, cudaStream_t st) {
+    GpbProfScope prof(GPB_KC_REDUCE, st);
     loglh_kernel<<<batch, 256, 0, st>>>(L, n_valid, ld, sL, y, sy, alpha, svec, info, out3);
     GPB_LAUNCH_CHECK("loglh_kernel");
     return GPB_OK;

@@ -330,13 +330,30 @@ class BatchEvaluator(object):
         self.kind = int(kind)
         self.nth = N_KP[self.kind] + 1
         self.n = int(np.asarray(x).size)
-        self.dx = D.to_device(x)
-        self.dy = D.to_device(y)
+        dev = D.require_cuda()
+        # pinned staging: host inputs cross PCIe asynchronously on the compute stream
+        self._hx = torch.empty(self.n, dtype=D.F64).pin_memory()
+        self._hy = torch.empty(self.n, dtype=D.F64).pin_memory()
+        self._hres = None
+        self.dx = torch.empty(self.n, dtype=D.F64, device=dev)
+        self.dy = torch.empty(self.n, dtype=D.F64, device=dev)
+        self.set_data(x, y)
         per = int(_lib.lib.gpb_eval_workspace_bytes(self.n, 1, 1))
         cap = max(1, int(workspace_gb * 2 ** 30) // per)
         self.max_batch = int(min(cap, max_batch or cap, 65535 // max(1, D.roundup(self.n) // D.NB)))
         self._ws = None
         self._ws_batch = 0
+
+    def set_data(self, x, y):
+        """(Re)upload the observations: numpy -> pinned staging -> HBM."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        if x.size != self.n or y.size != self.n:
+            raise ValueError("x and y must keep their length (%d)" % self.n)
+        self._hx.numpy()[:] = x
+        self._hy.numpy()[:] = y
+        self.dx.copy_(self._hx, non_blocking=True)
+        self.dy.copy_(self._hy, non_blocking=True)
 
     def _workspace(self, batch, want_grad):
         if self._ws is None or batch > self._ws_batch:
@@ -362,5 +379,11 @@ class BatchEvaluator(object):
 
     def eval(self, thetas, want_grad=True):
         """(log_lh[B], dloglh[B, n_theta], info[B]) as numpy arrays."""
-        r = D.to_host(self.eval_device(thetas, want_grad))
+        res = self.eval_device(thetas, want_grad)
+        if self._hres is None or self._hres.shape[0] < res.shape[0]:
+            self._hres = torch.empty(res.shape[0], 8, dtype=D.F64).pin_memory()
+        h = self._hres[:res.shape[0]]
+        h.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        r = h.numpy()
         return r[:, 0].copy(), r[:, 1:1 + self.nth].copy(), r[:, 7].astype(np.int64)

@@ -67,8 +67,8 @@ def log_lh(y, K, Kiy):
     info = D.izeros(1)
     call("gpb_potrf", D.ptr(L), npad, npad, 0, 1, D.ptr(W), npad, 0, None, 0, 0, D.ptr(info), D.stream_ptr())
     out = D.empty(3)
-    call("gpb_loglh", D.ptr(L), n, npad, D.ptr(D.to_device(y)), D.ptr(D.to_device(Kiy)), D.ptr(info),
-         D.ptr(out), D.stream_ptr())
+    dy, dKiy = D.to_device(y), D.to_device(Kiy)     # named: must outlive the launch
+    call("gpb_loglh", D.ptr(L), n, npad, D.ptr(dy), D.ptr(dKiy), D.ptr(info), D.ptr(out), D.stream_ptr())
     return float(D.to_host(out)[0])
 
 
@@ -77,17 +77,18 @@ def _brackets(y, Ki, Kj, Kiy, s):
     carray(y, 1, "y"); carray(Ki, 2, "Ki"); carray(Kj, 3, "Kj"); carray(Kiy, 1, "Kiy")
     n_p, n = Kj.shape[0], Kj.shape[1]
     dKi, dy, dKiy = D.mat_to_device(Ki, n, n), D.to_device(y), D.to_device(Kiy)
-    u = _gemv(dKi, n, n, n, dy) if False else None
-    # y^T Ki is (Ki^T y)^T: use a transposed product through trace/quadform primitives
     sc = _Scratch(n)
-    # row vector y^T Ki  ==  quadform building block: t0 = (Ki^T y)^T dK Kiy
-    KiT_y = D.empty(n)
-    call("gpb_gemv", D.ptr(dKi.t().contiguous()), n, n, n, D.ptr(dy), D.ptr(KiT_y), 1.0, 0.0, D.stream_ptr())
+    # y^T (Ki dK) Kiy = (Ki^T y)^T dK Kiy: one transposed mat-vec, then quadratic forms
+    dKiT = dKi.t().contiguous()
+    KiT_y = _gemv(dKiT, n, n, n, dy)
+    keep = [dKiT]
     for i in range(n_p):
         dKj = D.mat_to_device(Kj[i], n, n)
+        keep.append(dKj)
         sc.quadform(KiT_y, dKj, n, dKiy, n)
         sc.trace_prod(dKi, dKj, n, n)
-    eye_tr = sc.trace_prod(dKi, _eye(n), n, n)
+    eye = _eye(n)
+    sc.trace_prod(dKi, eye, n, n)
     dot = D.empty(1)
     call("gpb_gemv", D.ptr(KiT_y), 1, n, n, D.ptr(dKiy), D.ptr(dot), 1.0, 0.0, D.stream_ptr())
     v = sc.values()

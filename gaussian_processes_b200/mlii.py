@@ -52,12 +52,18 @@ def select_best(log_lh):
 
 
 def _evaluator(gp):
+    """One evaluator (device buffers + workspace) per GP object; new x / y arrays of the
+    same length are re-uploaded into it instead of rebuilding it."""
     ev = getattr(gp, "_batch_ev", None)
-    key = (id(gp._x), id(gp._y), type(gp.K).KIND)
-    if ev is None or ev[0] != key:
-        ev = (key, _engine.BatchEvaluator(key[2], gp._x, gp._y))
+    shape_key = (type(gp.K).KIND, gp._x.size)
+    data_key = (id(gp._x), id(gp._y))
+    if ev is None or ev[0] != shape_key:
+        ev = [shape_key, data_key, _engine.BatchEvaluator(shape_key[0], gp._x, gp._y)]
         gp._batch_ev = ev
-    return ev[1]
+    elif ev[1] != data_key:
+        ev[2].set_data(gp._x, gp._y)
+        ev[1] = data_key
+    return ev[2]
 
 
 def batch_eval(gp, thetas, grad=True):

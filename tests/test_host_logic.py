@@ -1,0 +1,172 @@
+"""Host-side semantics that need no GPU: parameter validation, copy / pickle state,
+memo bookkeeping, argument checking of the ext shims, sharding helpers.
+(reference behaviours: SURVEY Appendix C; gp/tests/test_gp.py:245-432,
+gp/tests/test_gaussian_kernel.py:155-189, test_periodic_kernel.py:206-246)"""
+import pickle
+from copy import copy, deepcopy
+
+import numpy as np
+import pytest
+
+import gaussian_processes_b200 as gpb
+from gaussian_processes_b200 import GP, GaussianKernel, PeriodicKernel
+from gaussian_processes_b200.mlii import shard_bounds, select_best
+from suite_util import make_xy, rand_params, seed
+
+
+def make_gp():
+    x, y = make_xy()
+    return GP(GaussianKernel(1, 1), x, y, s=1)
+
+
+@pytest.mark.parametrize("cls,names", [(GaussianKernel, "hw"), (PeriodicKernel, "hwp")])
+def test_kernel_params(cls, names):
+    seed()
+    for _ in range(20):
+        params = rand_params(*names)
+        k = cls(*params)
+        assert (k.params == np.array(params)).all()
+        k.params = params
+        assert (k.params == np.array(params)).all()
+        assert k.params is not k.params and k.params.dtype == np.float64
+    good = rand_params(*names)
+    for i in range(len(names)):
+        bad = list(good)
+        bad[i] = 0
+        with pytest.raises(ValueError):
+            cls(*bad)
+        k = cls(*good)
+        with pytest.raises(ValueError):
+            k.params = bad
+    with pytest.raises(ValueError):
+        cls(*good).set_param("nope", 1.0)
+
+
+@pytest.mark.parametrize("cls,params", [(GaussianKernel, (1.0, 0.5)), (PeriodicKernel, (1.0, 0.5, 2.0))])
+def test_kernel_copy_pickle(cls, params):
+    k1 = cls(*params)
+    for k2 in (k1.copy(), copy(k1), deepcopy(k1), pickle.loads(pickle.dumps(k1))):
+        assert k2 is not k1 and type(k2) is cls
+        assert (k2.params == k1.params).all()
+        for n in cls._names:
+            assert getattr(k1, n) is not getattr(k2, n)
+            assert type(getattr(k2, n)) is np.float64
+
+
+def test_kernel_api_surface():
+    g, p = GaussianKernel(1, 1), PeriodicKernel(1, 1, 1)
+    for n in ("K", "jacobian", "hessian", "dK_dh", "dK_dw", "d2K_dhdh", "d2K_dhdw", "d2K_dwdh", "d2K_dwdw"):
+        assert callable(getattr(g, n))
+    for a in "hwp":
+        assert callable(getattr(p, "dK_d%s" % a))
+        for b in "hwp":
+            assert callable(getattr(p, "d2K_d%sd%s" % (a, b)))
+    import sympy
+    assert isinstance(g.sym_K, sympy.Expr) and isinstance(p.sym_K, sympy.Expr)
+    assert set(gpb.__all__) >= {"ext", "GP", "Kernel", "PeriodicKernel", "GaussianKernel"}
+    assert set(gpb.ext.__all__) == {"gaussian_c", "periodic_c", "gp_c"}
+
+
+def test_gp_inputs_and_errors():
+    gp = make_gp()
+    assert gp.x.dtype == np.float64 and not gp.x.flags.writeable and not gp.y.flags.writeable
+    assert type(gp.s) is np.float64
+    assert (gp.params == np.array([1, 1, 1.0])).all()
+    with pytest.raises(ValueError):
+        gp.y = gp.y.copy()[:, None]                        # test_gp.py:282-286
+    x, y = make_xy()
+    with pytest.raises(ValueError):
+        GP(GaussianKernel(1, 1), x, y, s=-1)               # test_gp.py:289-295
+    gp = make_gp()
+    gp.set_param("h", 1)
+    gp.set_param("w", 0.2)
+    gp.set_param("s", 0.01)
+    assert gp.get_param("w") == 0.2 and gp.get_param("s") == 0.01
+    with pytest.raises(AttributeError):
+        gp.set_param("p", 1.1)                             # test_gp.py:425-432
+
+
+def test_memo_bookkeeping():
+    """del removes one key; every setter empties the cache (test_gp.py:245-279)."""
+    gp = make_gp()
+    for prop in ("Kxx", "Kxx_J", "Kxx_H", "Lxx", "inv_Kxx", "inv_Kxx_y", "log_lh", "lh",
+                 "dloglh_dtheta", "dlh_dtheta", "d2lh_dtheta2"):
+        assert isinstance(getattr(GP, prop), gpb.gp.memoprop)
+        gp._memoized[prop] = "cached"
+        assert getattr(gp, prop) == "cached"
+        delattr(gp, prop)
+        assert prop not in gp._memoized
+        with pytest.raises(AttributeError):
+            setattr(gp, prop, 1)
+    for prop, val in (("x", gp.x.copy() + 1), ("y", gp.y.copy() + 1), ("s", gp.s + 1), ("params", gp.params + 1)):
+        gp._memoized["Kxx"] = 1
+        setattr(gp, prop, val)
+        assert gp._memoized == {}
+    gp._memoized["Kxx"] = 1
+    gp.s = gp.s                                            # equal value: no reset
+    gp.x = gp.x.copy()
+    assert gp._memoized == {"Kxx": 1}
+    gp.set_param("w", 3.0)
+    assert gp._memoized == {}
+
+
+def test_gp_copy_semantics():
+    gp1 = make_gp()
+    gp1._memoized["log_lh"] = np.float64(-1.0)
+    for gp2 in (gp1.copy(deep=False), copy(gp1)):          # test_gp.py:351-370
+        assert gp1 is not gp2 and gp1._x is gp2._x and gp1._y is gp2._y
+        assert gp1._s is gp2._s and gp1.K is gp2.K
+    for gp2 in (gp1.copy(deep=True), deepcopy(gp1), pickle.loads(pickle.dumps(gp1))):   # :373-422
+        assert gp1 is not gp2 and gp1._x is not gp2._x and gp1._y is not gp2._y
+        assert gp1._s is not gp2._s and gp1.K is not gp2.K and gp1.K.params is not gp2.K.params
+        assert (gp1._x == gp2._x).all() and (gp1._y == gp2._y).all() and gp1._s == gp2._s
+        assert (gp1.K.params == gp2.K.params).all()
+        assert gp2._memoized == {"log_lh": -1.0}           # the memo is part of the state (gp.py:78-92)
+
+
+def test_ext_argument_validation():
+    """Cython-style buffer validation raises before any device work."""
+    from gaussian_processes_b200.ext import gaussian_c, periodic_c, gp_c
+    x = np.linspace(0, 1, 4)
+    with pytest.raises(ValueError):
+        gaussian_c.K(np.empty((4, 4), dtype=np.float32), x, x, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        gaussian_c.K(np.empty((4, 4)), x.astype(np.float32), x, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        gaussian_c.jacobian(np.empty((4, 4)), x, x, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        periodic_c.hessian(np.empty((3, 3, 4, 5)), x, x, 1.0, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        gaussian_c.K(np.empty((8, 4))[::2], x, x, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        gp_c.log_lh(x, np.eye(4, dtype=np.float32), x)
+    with pytest.raises(TypeError):
+        gaussian_c.K([[0.0]], x, x, 1.0, 1.0)
+
+
+def test_sharding_helpers():
+    for total in (0, 1, 7, 4096):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(total, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == total
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    assert select_best(np.array([-3.0, np.nan, -1.0, -1.0, -np.inf])) == 2
+    assert select_best(np.array([np.nan, -np.inf])) in (0, 1)
+    assert select_best(np.array([-np.inf, -np.inf])) == 0
+
+
+def test_install_as_gp():
+    import sys
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "gp" or k.startswith("gp.")}
+    try:
+        gpb.install_as_gp()
+        import gp
+        assert gp.GP is GP and gp.ext.gaussian_c is gpb.ext.gaussian_c
+        from gp.kernels import GaussianKernel as G2
+        assert G2 is GaussianKernel
+    finally:
+        for k in [k for k in sys.modules if k == "gp" or k.startswith("gp.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the public API and the C ABI) against the CPU
+oracle on the same seeded inputs, against the golden vectors produced by the
+unmodified reference, and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Tolerance (BASELINE.json north_star): scalars |d|/|ref| <= 1e-9,
+arrays ||d||_inf <= 1e-9 ||ref||_inf; identical -inf / 0 / NaN / exception behaviour."""
+import numpy as np
+import pytest
+
+import gaussian_processes_b200 as gpb
+from gaussian_processes_b200 import GP, GaussianKernel, PeriodicKernel
+from conftest import golden, assert_parity, synth_xy, RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def make_kernel(params):
+    return GaussianKernel(*params) if len(params) == 2 else PeriodicKernel(*params)
+
+
+def kind_of(oracle, kparams):
+    return oracle.GAUSSIAN if len(kparams) == 2 else oracle.PERIODIC
+
+
+# ------------------------------------------------------------------ builders
+@pytest.mark.parametrize("n1,n2", [(10, 10), (23, 16), (1, 7), (7, 1), (130, 67), (257, 300)])
+@pytest.mark.parametrize("kparams", [(1.3, 0.4), (0.7, 0.9, 1.7)])
+def test_builders_vs_oracle(oracle, n1, n2, kparams):
+    rng = np.random.RandomState(n1 * 1000 + n2)
+    x1, x2 = rng.uniform(-6, 6, n1), rng.uniform(-6, 6, n2)
+    k, kind = make_kernel(kparams), kind_of(oracle, kparams)
+    assert_parity(k(x1, x2), oracle.K(kind, x1, x2, kparams), 1e-13, "K")
+    assert_parity(k.jacobian(x1, x2), oracle.jacobian(kind, x1, x2, kparams), 1e-13, "J")
+    assert_parity(k.hessian(x1, x2), oracle.hessian(kind, x1, x2, kparams), 1e-12, "H")
+
+
+def test_builders_empty_inputs():
+    k = GaussianKernel(1.0, 1.0)
+    e, x = np.empty(0), np.linspace(0, 1, 3)
+    assert k(e, x).shape == (0, 3) and k(x, e).shape == (3, 0) and k.jacobian(e, e).shape == (2, 0, 0)
+
+
+def test_builders_vs_golden():
+    g = golden("kernels")
+    for t in range(4):
+        for tag, xa in (("g", g["x10"]), ("p", g["x16"])):
+            k = make_kernel(g["%s%d_params" % (tag, t)])
+            assert_parity(k(xa, xa), g["%s%d_K" % (tag, t)], 1e-13)
+            assert_parity(k.jacobian(xa, xa), g["%s%d_J" % (tag, t)], 1e-13)
+            assert_parity(k.hessian(xa, xa), g["%s%d_H" % (tag, t)], 1e-12)
+            assert_parity(k.hessian(g["xr"], xa), g["%s%d_Hr" % (tag, t)], 1e-12)
+    kz = GaussianKernel(*g["gz_params"])
+    K = kz(g["gz_x"], g["gz_x"])
+    assert ((K == 0) == (g["gz_K"] == 0)).all() and (K == 0).sum() > 0     # e < MIN -> exactly 0
+    assert ((kz.hessian(g["gz_x"], g["gz_x"]) == 0) == (g["gz_H"] == 0)).all()
+
+
+# ------------------------------------------------------------------ GP vs golden (reference outputs)
+FULL_KEYS = ["Kxx", "Kxx_J", "Kxx_H", "Lxx", "inv_Kxx", "inv_Kxx_y", "log_lh", "dloglh_dtheta",
+             "dlh_dtheta", "d2lh_dtheta2"]
+
+
+@pytest.mark.parametrize("name", ["gp_suite_g0", "gp_suite_g1", "gp_suite_g2", "gp_suite_p0",
+                                  "gp_suite_p1", "gp_suite_p2", "gp_c1"])
+def test_gp_vs_golden_small(name):
+    g = golden(name)
+    gp = GP(make_kernel(g["params"][:-1]), g["x"], g["y"], s=g["params"][-1])
+    cond = np.linalg.cond(g["Kxx"])
+    assert cond < 1e4                       # fixtures are well conditioned: the 1e-9 bar applies as is
+    for key in FULL_KEYS:
+        assert_parity(getattr(gp, key), g[key], RTOL, "%s/%s" % (name, key))
+    for key in ("mean", "cov", "dm_dtheta"):
+        assert_parity(getattr(gp, key)(g["xo"]), g[key], RTOL, "%s/%s" % (name, key))
+    assert_parity(gp.d2loglh_normalised(), g["d2lh_norm"], RTOL, "d2lh_norm")
+    assert float(gp.lh) == pytest.approx(float(g["lh"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("name", ["gp_g300", "gp_p257"])
+def test_gp_vs_golden_multiblock(name):
+    g = golden(name)
+    gp = GP(make_kernel(g["params"][:-1]), g["x"], g["y"], s=g["params"][-1])
+    assert_parity(gp.log_lh, g["log_lh"])
+    assert_parity(gp.dloglh_dtheta, g["dloglh_dtheta"])
+    assert_parity(gp.inv_Kxx_y, g["inv_Kxx_y"])
+    assert_parity(gp.mean(g["xo"]), g["mean"])
+    c = gp.cov(g["xo"])
+    assert np.max(np.abs(np.diag(c) - g["cov_diag"])) <= RTOL * float(g["cov_fro"])
+    assert_parity(c[0], g["cov_row0"], 1e-9 * float(g["cov_fro"]) / np.max(np.abs(g["cov_row0"])))
+    assert_parity(gp.dm_dtheta(g["xo"]), g["dm_dtheta"])
+    assert_parity(gp.d2loglh_normalised(), g["d2lh_norm"])
+    assert_parity(np.diag(gp.Lxx), g["Lxx_diag"])
+    assert_parity(np.diag(gp.inv_Kxx), g["inv_Kxx_diag"])
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_c2_vs_reference_values(n):
+    """BASELINE config C2 (N=4096) and its N=1024 sibling against the reference's own numbers."""
+    g = golden("gp_c2_n%d" % n)
+    x, y = synth_xy(n, 0)
+    gp = GP(GaussianKernel(*g["params"][:-1]), x, y, s=g["params"][-1])
+    assert_parity(gp.log_lh, g["log_lh"])
+    assert_parity(gp.dloglh_dtheta, g["dloglh_dtheta"])
+    assert gp.lh == 0 and type(gp.lh) is int                       # underflow -> int 0 (gp.py:393-394)
+    assert (gp.dlh_dtheta == 0).all() and (gp.d2lh_dtheta2 == 0).all()
+    assert_parity(gp.inv_Kxx_y, g["inv_Kxx_y"])
+    assert_parity(gp.mean(g["xo"]), g["mean"])
+    assert_parity(gp.cov(g["xo"]), g["cov"])
+    assert_parity(gp.dm_dtheta(g["xo"]), g["dm_dtheta"])
+    assert_parity(gp.d2loglh_normalised(), g["d2lh_norm"])
+    assert_parity(np.diag(gp.Lxx), g["Lxx_diag"])
+    assert_parity(np.diag(gp.inv_Kxx), g["inv_Kxx_diag"])
+
+
+# ------------------------------------------------------------------ GP vs oracle on seeded inputs
+@pytest.mark.parametrize("n,kparams,s,m", [
+    (1, (1.0, 0.5), 1.0, 3), (2, (1.0, 0.5), 0.5, 1), (127, (1.2, 0.3), 0.7, 50), (128, (1.2, 0.3), 0.7, 128),
+    (129, (0.8, 0.6), 0.9, 130), (640, (1.0, 0.5), 1.0, 200), (513, (1.0, 1.0, 1.0), 1.0, 77)])
+def test_gp_vs_oracle(oracle, n, kparams, s, m):
+    x, y = synth_xy(n, n)
+    xo = np.linspace(-2 * np.pi, 2 * np.pi, m)
+    gp = GP(make_kernel(kparams), x, y, s=s)
+    o = oracle.OracleGP(kind_of(oracle, kparams), kparams, x, y, s)
+    for key in ("Kxx", "Lxx", "inv_Kxx", "inv_Kxx_y", "log_lh", "dloglh_dtheta"):
+        assert_parity(getattr(gp, key), getattr(o, key), RTOL, key)
+    assert_parity(gp.mean(xo), o.mean(xo), RTOL, "mean")
+    assert_parity(gp.cov(xo), o.cov(xo), RTOL, "cov")
+    assert_parity(gp.dm_dtheta(xo), o.dm_dtheta(xo), RTOL, "dm")
+    assert_parity(gp.d2loglh_normalised(), o.d2lh_dtheta2_with(1.0, o.dloglh_dtheta), RTOL, "d2lh(lh=1)")
+    assert gp.mean(np.empty(0)).shape == (0,) and gp.cov(np.empty(0)).shape == (0, 0)
+    assert gp.dm_dtheta(np.empty(0)).shape == (len(kparams) + 1, 0)
+
+
+def test_logdet_clamp_matches_reference(oracle):
+    """logdet(Kxx) < MIN -> log_lh = -inf although the Cholesky succeeds; the
+    gradient is still finite (only LinAlgError gives NaN)."""
+    x, y = synth_xy(1024, 0)
+    gp = GP(GaussianKernel(1.0, 0.5), x, y, s=0.1)
+    o = oracle.OracleGP(oracle.GAUSSIAN, (1.0, 0.5), x, y, 0.1)
+    assert o.log_lh == -np.inf and gp.log_lh == -np.inf and gp.lh == 0
+    assert np.isfinite(gp.dloglh_dtheta).all()
+    assert_parity(gp.dloglh_dtheta, o.dloglh_dtheta, 1e-7, "dloglh at cond ~1e4")
+
+
+def test_nonfinite_inputs_raise_like_scipy():
+    x, y = synth_xy(16, 0)
+    y2 = y.copy()
+    y2[3] = np.nan
+    gp = GP(GaussianKernel(1.0, 0.5), x, y2, s=1.0)
+    with pytest.raises(ValueError):
+        gp.Lxx
+
+
+# ------------------------------------------------------------------ C ABI level
+def test_host_abi_eval_matches_object_path():
+    import ctypes
+    from gaussian_processes_b200 import _lib
+    x, y = synth_xy(300, 0)
+    th = np.array([[1.0, 0.5, 1.0], [1.3, 0.4, 0.8]])
+    res = np.empty((2, 8))
+    _lib.call("gpb_gp_eval_host", 0, th.ctypes.data_as(_lib.dp), 2, x.ctypes.data_as(_lib.dp),
+              y.ctypes.data_as(_lib.dp), 300, 1, res.ctypes.data_as(_lib.dp))
+    for b in range(2):
+        gp = GP(GaussianKernel(*th[b, :2]), x, y, s=th[b, 2])
+        assert_parity(res[b, 0], gp.log_lh, 1e-13)
+        assert_parity(res[b, 1:4], gp.dloglh_dtheta, 1e-12)
+        assert res[b, 7] == 0
+
+
+def test_ext_gp_c_dropins():
+    from gaussian_processes_b200.ext import gp_c
+    g = golden("gp_suite_g0")
+    y, s = g["y"], float(g["params"][-1])
+    assert_parity(gp_c.log_lh(y, g["Kxx"], g["inv_Kxx_y"]), g["log_lh"])
+    out = np.empty(3)
+    gp_c.dloglh_dtheta(y, g["inv_Kxx"], g["Kxx_J"], g["inv_Kxx_y"], s, out)
+    assert_parity(out, g["dloglh_dtheta"])
+    gp_c.dlh_dtheta(y, g["inv_Kxx"], g["Kxx_J"], g["inv_Kxx_y"], s, float(g["lh"]), out)
+    assert_parity(out, g["dlh_dtheta"])
+    o2 = np.empty((3, 3))
+    gp_c.d2lh_dtheta2(y, g["inv_Kxx"], g["Kxx_J"], g["Kxx_H"], g["inv_Kxx_y"], s, float(g["lh"]),
+                      g["dlh_dtheta"], o2)
+    assert_parity(o2, g["d2lh_dtheta2"])
+    k = GaussianKernel(*g["params"][:-1])
+    dm = np.empty((3, g["xo"].size))
+    gp_c.dm_dtheta(y, g["inv_Kxx"], g["Kxx_J"], k.jacobian(g["xo"], g["x"]), k(g["xo"], g["x"]), s, dm)
+    assert_parity(dm, g["dm_dtheta"])
+    gp = golden("gp_suite_p1")
+    assert_parity(gp_c.log_lh(gp["y"], gp["Kxx"], gp["inv_Kxx_y"]), gp["log_lh"])
+
+
+# ------------------------------------------------------------------ batched search
+def test_batch_eval_and_fit_mlii_vs_oracle(oracle):
+    x, y = synth_xy(200, 7)
+    rng = np.random.RandomState(11)
+    B = 24
+    cand = np.stack([rng.uniform(0.5, 2, B), rng.uniform(np.pi / 32, np.pi / 2, B), rng.uniform(0.75, 1.5, B)], axis=1)
+    gp = GP(GaussianKernel(1.0, 1.0), x, y, s=1.0)
+    llh, grad = gp.batch_eval(cand)
+    best, ollh, ograd = oracle.oracle_fit_mlii(oracle.GAUSSIAN, x, y, cand)
+    assert_parity(llh, ollh)
+    for b in range(B):
+        assert_parity(grad[b], ograd[b], RTOL, "grad[%d]" % b)
+    res = gp.fit_MLII(cand)
+    assert res.best_index == best and np.array_equal(gp.params, cand[best])
+    assert_parity(gp.log_lh, ollh[best])
+    kp = np.stack([rng.uniform(0.5, 2, 5), rng.uniform(0.5, 1.5, 5), rng.uniform(0.5, 3, 5), rng.uniform(0.75, 1.5, 5)], axis=1)
+    gpp = GP(PeriodicKernel(1.0, 1.0, 1.0), x, y, s=1.0)
+    l2, g2 = gpp.batch_eval(kp)
+    _, ol2, og2 = oracle.oracle_fit_mlii(oracle.PERIODIC, x, y, kp)
+    assert_parity(l2, ol2)
+    assert_parity(g2, og2)
+
+
+def test_batch_eval_failure_rows(oracle):
+    """A candidate whose Kxx is not PD gives -inf / NaN in its row only; the clamp row gives
+    -inf with a finite gradient (reference semantics, gp.py:362-365, 424-428)."""
+    from suite_util import INVALID_X, INVALID_Y, INVALID_H, INVALID_W
+    gp = GP(GaussianKernel(1.0, 1.0), INVALID_X, INVALID_Y, s=0.5)
+    cand = np.array([[1.0, 0.5, 0.5], [INVALID_H, INVALID_W, 0.0], [0.7, 0.3, 0.2]])
+    llh, grad = gp.batch_eval(cand)
+    assert llh[1] == -np.inf and np.isnan(grad[1]).all()
+    for b in (0, 2):
+        o = oracle.OracleGP(oracle.GAUSSIAN, cand[b, :2], INVALID_X, INVALID_Y, cand[b, 2])
+        assert_parity(llh[b], o.log_lh)
+        assert_parity(grad[b], o.dloglh_dtheta)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_n4096():
+    """At the headline size the oracle takes minutes; use size-independent identities:
+    K * Ki = I, L L^T = K, K alpha = y, symmetric Ki, and the batched evaluator agreeing
+    with the object path."""
+    n = 4096
+    x, y = synth_xy(n, 0)
+    gp = GP(GaussianKernel(1.1, 0.45), x, y, s=0.9)
+    K, L, Ki, a = gp.Kxx, gp.Lxx, gp.inv_Kxx, gp.inv_Kxx_y
+    assert np.array_equal(L, np.tril(L))
+    scale = np.max(np.abs(K))
+    assert np.max(np.abs(L @ L.T - K)) <= 1e-12 * scale
+    assert np.max(np.abs(K @ Ki - np.eye(n))) <= 1e-10
+    assert np.max(np.abs(Ki - Ki.T)) <= 1e-13 * np.max(np.abs(Ki))
+    assert np.max(np.abs(K @ a - y)) <= 1e-11 * np.max(np.abs(y))
+    llh, grad = gp.batch_eval(np.array([gp.params, gp.params]))
+    assert_parity(llh[0], gp.log_lh, 1e-13)
+    assert_parity(grad[0], gp.dloglh_dtheta, 1e-12)
+    assert llh[0] == llh[1] and np.array_equal(grad[0], grad[1])     # deterministic reductions
+    # gradient against a central difference of the object's own log_lh (test_gp.py:75-98 at scale)
+    for i, name in enumerate(("h", "w", "s")):
+        g0, g1 = gp.copy(), gp.copy()
+        g0.set_param(name, gp.params[i] - 1e-5)
+        g1.set_param(name, gp.params[i] + 1e-5)
+        fd = (g1.log_lh - g0.log_lh) / 2e-5
+        assert abs(fd - gp.dloglh_dtheta[i]) <= 1e-5 * abs(fd) + 1e-4
+
+
+def test_periodic_posterior_sharded_blocks(oracle):
+    """C3-shaped (scaled to what the oracle finishes in seconds): Periodic GP, the posterior of a
+    block of test points equals the same rows/cols of the full posterior (test points shard)."""
+    n, m = 1536, 600
+    x, y = synth_xy(n, 2)
+    xo = np.linspace(-2 * np.pi, 2 * np.pi, m)
+    gp = GP(PeriodicKernel(1.0, 1.0, 1.0), x, y, s=1.0)
+    o = oracle.OracleGP(oracle.PERIODIC, (1.0, 1.0, 1.0), x, y, 1.0)
+    mean, cov = gp.mean(xo), gp.cov(xo)
+    assert_parity(mean, o.mean(xo))
+    assert_parity(cov, o.cov(xo))
+    lo, hi = 150, 420
+    assert_parity(gp.mean(xo[lo:hi]), mean[lo:hi], 1e-13)
+    assert_parity(gp.cov(xo[lo:hi]), cov[lo:hi, lo:hi], 1e-12)
+    assert_parity(gp.Kxx_J, o.Kxx_J, 1e-13)
