@@ -395,11 +395,13 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     const int T = (int)(n / GPB_NB);
     for (int k = 0; k < T; k++) {
         const long long o = (long long)k * GPB_NB;
-        GpbProfScope prof(GPB_KC_DIAG, st);
-        potrf_diag_kernel<<<batch, 256, DIAG_SMEM, st>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
-                                                         V ? V + o * ldv + o : nullptr, ldv, sV, info,
-                                                         (int)o);
-        GPB_LAUNCH_CHECK("potrf_diag_kernel");
+        {
+            GpbProfScope prof(GPB_KC_DIAG, st);
+            potrf_diag_kernel<<<batch, 256, DIAG_SMEM, st>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
+                                                             V ? V + o * ldv + o : nullptr, ldv, sV, info,
+                                                             (int)o);
+            GPB_LAUNCH_CHECK("potrf_diag_kernel");
+        }
         const int rem = (T - 1 - k) * GPB_NB;
         if (rem == 0) break;
         GpbGemm g = gpb_gemm_default();            // panel: A_ik <- A_ik * W_kk^T (in place)
