@@ -63,6 +63,9 @@ _PROTOS = {
     "gpb_gp_eval_host": (c_int, [c_int, dp, c_int, dp, dp, _i64, c_int, dp]),
     "gpb_kernel_slices_host": (c_int, [c_int, c_uint, vp, vp, _i64, vp, _i64, dp]),
     "gpb_microbench_fp64": (c_int, [c_int, c_int, dp, dp]),
+    "gpb_set_option": (c_int, [c_char_p, c_int]),
+    "gpb_profile_enable": (None, [c_int]),
+    "gpb_profile_read": (c_int, [c_int, dp, POINTER(c_int64)]),
 }
 for _n in ("K", "jacobian", "hessian", "dK_dh", "dK_dw", "d2K_dhdh", "d2K_dhdw", "d2K_dwdh", "d2K_dwdw"):
     _PROTOS["gpb_gaussian_" + _n] = (c_int, _SIG_G)
@@ -92,6 +95,11 @@ def check(status, what=""):
 
 def call(name, *args):
     check(getattr(lib, name)(*args), name)
+
+
+def set_option(name, value):
+    """Tuning knobs: eval_streams, gemm_bm, potrf_inner (0 = default)."""
+    call("gpb_set_option", name.encode(), int(value))
 
 
 def darr(values):

@@ -1,6 +1,7 @@
 // api.cu -- extern "C" surface of libgpb200.so (declared in include/gpb200.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "../../include/gpb200.h"
@@ -57,6 +58,75 @@ static void prof_collect() {
         cudaEventDestroy(p.b);
     }
     g_prof_pairs.clear();
+}
+
+// ---- run-time options -------------------------------------------------------------
+struct GpbOption { const char* name; const char* env; int value; bool env_read; };
+static GpbOption g_options[] = {
+    {"eval_streams", "GPB_EVAL_STREAMS", 0, false},   // candidate groups evaluated on concurrent streams
+    {"gemm_bm", "GPB_GEMM_BM", 0, false},             // 64 (2 CTAs/SM) or 128 row tiles
+    {"potrf_inner", "GPB_POTRF_INNER", 0, false},     // 128-columns per outer Cholesky panel
+};
+int gpb_get_option(const char* name) {
+    for (auto& o : g_options)
+        if (strcmp(o.name, name) == 0) {
+            if (!o.env_read) {
+                o.env_read = true;
+                const char* e = getenv(o.env);
+                if (e && o.value == 0) o.value = atoi(e);
+            }
+            return o.value;
+        }
+    return 0;
+}
+
+// ---- pinned staging ring: small host->device parameter uploads without stalling ------
+struct PinSlot { void* host; size_t cap; cudaEvent_t ev; bool used; };
+static PinSlot g_pin[32];
+static int g_pin_next = 0;
+static int pin_acquire(size_t bytes, int* slot, void** host) {
+    const int sidx = g_pin_next++ % 32;
+    PinSlot& p = g_pin[sidx];
+    if (p.used) GPB_CUDA(cudaEventSynchronize(p.ev));
+    if (p.cap < bytes) {
+        if (p.host) GPB_CUDA(cudaFreeHost(p.host));
+        p.host = nullptr; p.cap = 0;
+        GPB_CUDA(cudaHostAlloc(&p.host, bytes, cudaHostAllocDefault));
+        p.cap = bytes;
+    }
+    if (!p.ev) GPB_CUDA(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
+    *slot = sidx;
+    *host = p.host;
+    return GPB_OK;
+}
+static int pin_release(int slot, cudaStream_t st) {
+    GPB_CUDA(cudaEventRecord(g_pin[slot].ev, st));
+    g_pin[slot].used = true;
+    return GPB_OK;
+}
+
+// ---- internal streams for concurrent candidate groups ---------------------------------
+#define GPB_MAX_GROUPS 8
+static cudaStream_t g_gstream[GPB_MAX_GROUPS];
+static cudaEvent_t g_fork_ev, g_join_ev[GPB_MAX_GROUPS];
+static bool g_gstream_init = false;
+static int gstreams_init() {
+    if (g_gstream_init) return GPB_OK;
+    for (int i = 0; i < GPB_MAX_GROUPS; i++) {
+        GPB_CUDA(cudaStreamCreateWithFlags(&g_gstream[i], cudaStreamNonBlocking));
+        GPB_CUDA(cudaEventCreateWithFlags(&g_join_ev[i], cudaEventDisableTiming));
+    }
+    GPB_CUDA(cudaEventCreateWithFlags(&g_fork_ev, cudaEventDisableTiming));
+    g_gstream_init = true;
+    return GPB_OK;
+}
+static int eval_groups(int64_t n, int batch) {
+    int g = gpb_get_option("eval_streams");
+    if (g < 1) g = 4;
+    if (g > GPB_MAX_GROUPS) g = GPB_MAX_GROUPS;
+    if (n < 512) g = 1;                  // tiny problems: one launch group is already latency-bound
+    if (g > batch) g = batch;
+    return g;
 }
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -143,6 +213,12 @@ void gpb_profile_enable(int on) {
     prof_collect();
     g_gpb_profile = on;
     if (on) for (int c = 0; c < GPB_KC_COUNT; c++) { g_prof_ms[c] = 0.0; g_prof_n[c] = 0; }
+}
+int gpb_set_option(const char* name, int value) {
+    for (auto& o : g_options)
+        if (strcmp(o.name, name) == 0) { o.value = value; o.env_read = true; return GPB_OK; }
+    gpb_set_error("gpb_set_option: unknown option %s", name);
+    return GPB_ERR_ARG;
 }
 int gpb_profile_read(int cls, double* ms, int64_t* launches) {
     GPB_REQUIRE(cls >= 0 && cls < GPB_KC_COUNT, "bad kernel class");
@@ -256,32 +332,35 @@ int gpb_quadform(const double* u, const double* M, int64_t ldm, const double* v,
 }
 
 size_t gpb_eval_workspace_bytes(int64_t n, int batch, int want_grad) {
-    return carve(nullptr, n, batch, want_grad).bytes;
+    const int G = eval_groups(n, batch);
+    const int gb = (batch + G - 1) / G;
+    return (size_t)G * carve(nullptr, n, gb, want_grad).bytes;
 }
 
-int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, const double* y, int64_t n,
-                int want_grad, void* workspace, size_t workspace_bytes, double* result, void* stream) {
-    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
-    GPB_REQUIRE(batch >= 1 && n >= 1 && thetas && x && y && workspace && result, "bad argument");
-    EvalWs w = carve((char*)workspace, n, batch, want_grad);
-    GPB_REQUIRE(w.bytes <= workspace_bytes, "workspace too small (see gpb_eval_workspace_bytes)");
-    GPB_REQUIRE((uintptr_t)workspace % 256 == 0, "workspace must be 256-byte aligned");
-    cudaStream_t st = S(stream);
+// one group of candidates on one stream
+static int eval_group(int kind, const double* thetas, int batch, const double* x, const double* y, int64_t n,
+                      int want_grad, char* wsbase, double* result, cudaStream_t st) {
+    EvalWs w = carve(wsbase, n, batch, want_grad);
     const long long np_ = roundup(n, GPB_NB);
     const long long mstride = np_ * np_;
     const int nth = gpb_n_kparams(kind) + 1;
 
-    std::vector<KParams> hp((size_t)batch);
+    int slot;
+    void* hostp;
+    int stt = pin_acquire(sizeof(KParams) * batch, &slot, &hostp);
+    if (stt) return stt;
+    KParams* hp = (KParams*)hostp;
     for (int b = 0; b < batch; b++) gpb_make_kparams(&hp[b], kind, thetas + (long long)b * nth, thetas[(long long)b * nth + nth - 1]);
-    GPB_CUDA(cudaMemcpyAsync(w.Pb, hp.data(), sizeof(KParams) * batch, cudaMemcpyHostToDevice, st));
-    GPB_CUDA(cudaStreamSynchronize(st));   // hp is a stack-lifetime staging buffer
+    GPB_CUDA(cudaMemcpyAsync(w.Pb, hp, sizeof(KParams) * batch, cudaMemcpyHostToDevice, st));
+    stt = pin_release(slot, st);
+    if (stt) return stt;
     GPB_CUDA(cudaMemsetAsync(w.ypad, 0, np_ * 8, st));
     GPB_CUDA(cudaMemcpyAsync(w.ypad, y, n * 8, cudaMemcpyDeviceToDevice, st));
 
     // Kxx + s^2 I straight into the factorisation buffer, identity in the pad
     double* outs[GPB_MAX_SLICES] = {nullptr};
     outs[0] = w.L;
-    int stt = gpb_launch_build(kind, nullptr, w.Pb, batch, x, n, x, n, np_, np_, outs, np_, mstride, 1, 1, st);
+    stt = gpb_launch_build(kind, nullptr, w.Pb, batch, x, n, x, n, np_, np_, outs, np_, mstride, 1, 1, st);
     if (stt) return stt;
     stt = gpb_launch_potrf(w.L, np_, np_, mstride, batch, w.W, np_, mstride, want_grad ? w.V : nullptr, np_, mstride, w.info, st);
     if (stt) return stt;
@@ -301,6 +380,36 @@ int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, cons
     }
     eval_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.out3, w.out8, w.info, w.Pb, kind, want_grad, batch, result);
     GPB_LAUNCH_CHECK("eval_finalize_kernel");
+    return GPB_OK;
+}
+
+int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, const double* y, int64_t n,
+                int want_grad, void* workspace, size_t workspace_bytes, double* result, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(batch >= 1 && n >= 1 && thetas && x && y && workspace && result, "bad argument");
+    GPB_REQUIRE(gpb_eval_workspace_bytes(n, batch, want_grad) <= workspace_bytes, "workspace too small (see gpb_eval_workspace_bytes)");
+    GPB_REQUIRE((uintptr_t)workspace % 256 == 0, "workspace must be 256-byte aligned");
+    cudaStream_t st = S(stream);
+    const int nth = gpb_n_kparams(kind) + 1;
+    const int G = eval_groups(n, batch);
+    if (G == 1) return eval_group(kind, thetas, batch, x, y, n, want_grad, (char*)workspace, result, st);
+    // Candidates are independent: groups run on concurrent streams so that one group's serial
+    // diagonal-block / panel kernels overlap another group's trailing-update GEMMs.
+    int stt = gstreams_init();
+    if (stt) return stt;
+    const int gb = (batch + G - 1) / G;
+    const size_t gbytes = carve(nullptr, n, gb, want_grad).bytes;
+    GPB_CUDA(cudaEventRecord(g_fork_ev, st));
+    for (int g = 0; g < G; g++) {
+        const int b0 = g * gb, b1 = (b0 + gb < batch) ? b0 + gb : batch;
+        if (b1 <= b0) break;
+        GPB_CUDA(cudaStreamWaitEvent(g_gstream[g], g_fork_ev, 0));
+        stt = eval_group(kind, thetas + (long long)b0 * nth, b1 - b0, x, y, n, want_grad,
+                         (char*)workspace + (size_t)g * gbytes, result + (long long)b0 * 8, g_gstream[g]);
+        if (stt) return stt;
+        GPB_CUDA(cudaEventRecord(g_join_ev[g], g_gstream[g]));
+        GPB_CUDA(cudaStreamWaitEvent(st, g_join_ev[g], 0));
+    }
     return GPB_OK;
 }
 

@@ -16,44 +16,64 @@
 // tiles, 64 fp64 accumulators per thread), 4-stage cp.async pipeline (160 KB smem,
 // one CTA per SM).  All extents are multiples of the tile (buffers are padded by the
 // host layer), so there is no edge predication in the main loop.
+#include <stdlib.h>
 #include "common.cuh"
 #include "launch.h"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int BN = 128, BK = 16;
 constexpr int LDS = BK + 4;   // padded row stride (doubles): conflict-free 8-byte fragment loads
-constexpr int TILE_DOUBLES = BM * LDS;
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_DOUBLES * 8;
 
+// Two tile shapes share the code:
+//   BM = 128: 256 threads, 4 stages (160 KB smem), one CTA per SM
+//   BM =  64: 128 threads, 3 stages ( 90 KB smem), two CTAs per SM -- the epilogue / prologue of
+//             one CTA overlaps the main loop of the other (short-K trailing updates)
+template <int BM> struct TileCfg {
+    static constexpr int THREADS = BM * 2;
+    static constexpr int STAGES = (BM == 128) ? 4 : 3;
+    static constexpr int A_DOUBLES = BM * LDS;
+    static constexpr int B_DOUBLES = BN * LDS;
+    static constexpr int SMEM_BYTES = STAGES * (A_DOUBLES + B_DOUBLES) * 8;
+    static constexpr int MIN_CTAS = (BM == 128) ? 1 : 2;
+};
+
+template <int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile(double* sdst, const double* g, long long ld, int tid) {
-    // 128 rows x 16 doubles = 1024 chunks of 16 B; 256 threads x 4
+    // ROWS x 16 doubles = ROWS*8 chunks of 16 B
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int c = tid + q * 256;
+    for (int q = 0; q < ROWS * 8 / THREADS; q++) {
+        const int c = tid + q * THREADS;
         const int row = c >> 3, ch = c & 7;
         cp_async16(sdst + row * LDS + ch * 2, g + (long long)row * ld + ch * 2);
     }
 }
 
-__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GpbGemm p) {
+template <int BM>
+__global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) gemm_nt_kernel(const GpbGemm p) {
+    using Cfg = TileCfg<BM>;
+    constexpr int STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
-    double* Bs = smem + STAGES * TILE_DOUBLES;
+    double* Bs = smem + STAGES * Cfg::A_DOUBLES;
 
     // ---- tile coordinates -------------------------------------------------
     int ti, tj;
+    bool diag_tile = false;
     if (p.lower_only) {
-        // blockIdx.x enumerates lower-triangular tile pairs, longest rows first when
-        // heavy_first (k-range grows with the row for upper-triangular operands)
-        const int t = blockIdx.x;
+        // blockIdx.x enumerates the tiles that touch the lower triangle, by 128-row groups:
+        // group q holds (128/BM) row tiles with q+1 column tiles each.
+        constexpr int RPG = 128 / BM;
+        const int t = blockIdx.x / RPG, sub = blockIdx.x % RPG;
         int i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
         while ((long long)(i + 1) * (i + 2) / 2 <= t) i++;
         while ((long long)i * (i + 1) / 2 > t) i--;
-        ti = i;
         tj = t - i * (i + 1) / 2;
+        ti = i * RPG + sub;
+        diag_tile = (tj == i);
     } else {
-        ti = blockIdx.x;
+        // longest k-range first: for a lower-triangular A the work grows with the row
+        ti = (p.a_tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
         tj = blockIdx.y;
     }
     const int m0 = ti * BM, n0 = tj * BN;
@@ -72,7 +92,7 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GpbGemm p) {
     const int nk = (kend > kbeg) ? (kend - kbeg) / BK : 0;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm = wid >> 1, wn = wid & 1;          // 4 x 2 warps
+    const int wm = wid >> 1, wn = wid & 1;          // (BM/32) x 2 warps, warp tile 32 x 64
     const int g = lane >> 2, t = lane & 3;
 
     double acc[4][8][2];
@@ -85,8 +105,8 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GpbGemm p) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < nk) {
-            load_tile(As + s * TILE_DOUBLES, A + kbeg + s * BK, p.lda, tid);
-            load_tile(Bs + s * TILE_DOUBLES, B + kbeg + s * BK, p.ldb, tid);
+            load_tile<BM, THREADS>(As + s * Cfg::A_DOUBLES, A + kbeg + s * BK, p.lda, tid);
+            load_tile<BN, THREADS>(Bs + s * Cfg::B_DOUBLES, B + kbeg + s * BK, p.ldb, tid);
         }
         cp_async_commit();
     }
@@ -99,13 +119,13 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GpbGemm p) {
             const int nx = kt + STAGES - 1;
             if (nx < nk) {
                 const int slot = nx % STAGES;
-                load_tile(As + slot * TILE_DOUBLES, A + kbeg + nx * BK, p.lda, tid);
-                load_tile(Bs + slot * TILE_DOUBLES, B + kbeg + nx * BK, p.ldb, tid);
+                load_tile<BM, THREADS>(As + slot * Cfg::A_DOUBLES, A + kbeg + nx * BK, p.lda, tid);
+                load_tile<BN, THREADS>(Bs + slot * Cfg::B_DOUBLES, B + kbeg + nx * BK, p.ldb, tid);
             }
             cp_async_commit();
         }
-        const double* as = As + (kt % STAGES) * TILE_DOUBLES + (wm * 32 + g) * LDS + t;
-        const double* bs = Bs + (kt % STAGES) * TILE_DOUBLES + (wn * 64 + g) * LDS + t;
+        const double* as = As + (kt % STAGES) * Cfg::A_DOUBLES + (wm * 32 + g) * LDS + t;
+        const double* bs = Bs + (kt % STAGES) * Cfg::B_DOUBLES + (wn * 64 + g) * LDS + t;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; kk++) {
             double a[4], b[8];
@@ -124,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GpbGemm p) {
     // ---- epilogue -----------------------------------------------------------------
     double* C = p.C + bz * p.sC + bt * p.tC;
     double* Ct = p.Ct ? p.Ct + bz * p.sCt + bt * p.tCt : nullptr;
-    const bool mirror = (Ct != nullptr) && !(p.lower_only && ti == tj && Ct == C);
+    const bool mirror = (Ct != nullptr) && !(p.lower_only && diag_tile && Ct == C);
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
@@ -150,31 +170,40 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GpbGemm p) {
 
 }  // namespace
 
-// `batch` = outer batch count; the grid's z extent is batch * p.nb1
-int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st) {
-    GPB_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0, "empty problem");
-    GPB_REQUIRE(p.M % BM == 0 && p.N % BN == 0 && p.K % BK == 0, "extents must be multiples of the 128x128x16 tile");
-    GPB_REQUIRE(p.lda % 2 == 0 && p.ldb % 2 == 0 && p.ldc % 2 == 0, "leading dimensions must be even");
-    GPB_REQUIRE(((uintptr_t)p.A % 16 == 0) && ((uintptr_t)p.B % 16 == 0) && ((uintptr_t)p.C % 16 == 0), "operands must be 16-byte aligned");
-    GPB_REQUIRE(p.sA % 2 == 0 && p.sB % 2 == 0 && p.sC % 2 == 0, "batch strides must be even");
-    GPB_REQUIRE(p.tA % 2 == 0 && p.tB % 2 == 0 && p.tC % 2 == 0 && p.nb1 >= 1, "inner batch strides must be even");
+
+template <int BM>
+static int launch_cfg(const GpbGemm& p, int batch, cudaStream_t st) {
+    using Cfg = TileCfg<BM>;
     static bool attr_set = false;
     if (!attr_set) {
-        GPB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     dim3 grid;
     const int tm = p.M / BM, tn = p.N / BN;
     if (p.lower_only) {
-        GPB_REQUIRE(tm == tn, "lower_only needs a square tile grid");
-        grid = dim3((unsigned)((long long)tm * (tm + 1) / 2), 1, (unsigned)(batch * p.nb1));
+        GPB_REQUIRE(p.M == p.N, "lower_only needs a square output");
+        grid = dim3((unsigned)((long long)tn * (tn + 1) / 2 * (128 / BM)), 1, (unsigned)(batch * p.nb1));
     } else {
         GPB_REQUIRE(tn <= 65535, "too many column tiles");
         grid = dim3((unsigned)tm, (unsigned)tn, (unsigned)(batch * p.nb1));
     }
-    GPB_REQUIRE(batch >= 1 && (long long)batch * p.nb1 <= 65535, "bad batch");
     GpbProfScope prof(GPB_KC_GEMM, st);
-    gemm_nt_kernel<<<grid, 256, SMEM_BYTES, st>>>(p);
+    gemm_nt_kernel<BM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
     GPB_LAUNCH_CHECK("gemm_nt_kernel");
     return GPB_OK;
+}
+
+// `batch` = outer batch count; the grid's z extent is batch * p.nb1
+int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st) {
+    GPB_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0, "empty problem");
+    GPB_REQUIRE(p.M % 128 == 0 && p.N % BN == 0 && p.K % BK == 0, "extents must be multiples of the 128x128x16 tile");
+    GPB_REQUIRE(p.lda % 2 == 0 && p.ldb % 2 == 0 && p.ldc % 2 == 0, "leading dimensions must be even");
+    GPB_REQUIRE(((uintptr_t)p.A % 16 == 0) && ((uintptr_t)p.B % 16 == 0) && ((uintptr_t)p.C % 16 == 0), "operands must be 16-byte aligned");
+    GPB_REQUIRE(p.sA % 2 == 0 && p.sB % 2 == 0 && p.sC % 2 == 0, "batch strides must be even");
+    GPB_REQUIRE(p.tA % 2 == 0 && p.tB % 2 == 0 && p.tC % 2 == 0 && p.nb1 >= 1, "inner batch strides must be even");
+    GPB_REQUIRE(batch >= 1 && (long long)batch * p.nb1 <= 65535, "bad batch");
+    int bm = gpb_get_option("gemm_bm");
+    if (bm != 64 && bm != 128) bm = 64;     // default: two co-resident 64x128 CTAs per SM
+    return bm == 128 ? launch_cfg<128>(p, batch, st) : launch_cfg<64>(p, batch, st);
 }

@@ -35,6 +35,9 @@ inline GpbGemm gpb_gemm_default() {
 
 int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st);
 
+// run-time tuning knobs (api.cu): "eval_streams", "gemm_bm", "potrf_inner"; 0 = default
+int gpb_get_option(const char* name);
+
 int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, const double* x1,
                      long long n1, const double* x2, long long n2, long long rows, long long cols,
                      double* const* out, long long ld, long long bstride, int add_diag,

@@ -393,33 +393,58 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     }
     GPB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
     const int T = (int)(n / GPB_NB);
-    for (int k = 0; k < T; k++) {
-        const long long o = (long long)k * GPB_NB;
-        {
-            GpbProfScope prof(GPB_KC_DIAG, st);
-            potrf_diag_kernel<<<batch, 256, DIAG_SMEM, st>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
-                                                             V ? V + o * ldv + o : nullptr, ldv, sV, info,
-                                                             (int)o);
-            GPB_LAUNCH_CHECK("potrf_diag_kernel");
+    // Two-level blocking: an outer panel of `inner` 128-columns is factored left-looking
+    // (skinny column updates with K = q*128), then ONE trailing update with K = inner*128
+    // touches the rest of the matrix -- half (or a quarter) as many passes over the trailing
+    // matrix as a plain 128-wide right-looking sweep, each with a longer DMMA main loop.
+    int inner = gpb_get_option("potrf_inner");
+    if (inner < 1) inner = 2;
+    for (int k0 = 0; k0 < T; k0 += inner) {
+        const int kw = (T - k0 < inner) ? (T - k0) : inner;
+        const long long p0 = (long long)k0 * GPB_NB;
+        for (int q = 0; q < kw; q++) {
+            const int k = k0 + q;
+            const long long o = (long long)k * GPB_NB;
+            if (q > 0) {                               // A[k:, k] -= L[k:, k0..k) * L[k, k0..k)^T
+                GpbGemm c = gpb_gemm_default();
+                c.A = A + o * ld + p0; c.lda = ld; c.sA = sA;
+                c.B = A + o * ld + p0; c.ldb = ld; c.sB = sA;
+                c.C = A + o * ld + o; c.ldc = ld; c.sC = sA;
+                c.M = (T - k) * GPB_NB; c.N = GPB_NB; c.K = q * GPB_NB;
+                c.alpha = -1.0; c.beta = 1.0;
+                int stt = gpb_launch_gemm(c, batch, st);
+                if (stt != GPB_OK) return stt;
+            }
+            {
+                GpbProfScope prof(GPB_KC_DIAG, st);
+                potrf_diag_kernel<<<batch, 256, DIAG_SMEM, st>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
+                                                                 V ? V + o * ldv + o : nullptr, ldv, sV, info,
+                                                                 (int)o);
+                GPB_LAUNCH_CHECK("potrf_diag_kernel");
+            }
+            const int rem = (T - 1 - k) * GPB_NB;
+            if (rem == 0) break;
+            GpbGemm g = gpb_gemm_default();            // panel: A_ik <- A_ik * W_kk^T (in place)
+            g.A = A + (o + GPB_NB) * ld + o; g.lda = ld; g.sA = sA;
+            g.B = W + o * ldw + o; g.ldb = ldw; g.sB = sW;
+            g.C = A + (o + GPB_NB) * ld + o; g.ldc = ld; g.sC = sA;
+            g.M = rem; g.N = GPB_NB; g.K = GPB_NB;
+            g.b_tri = 1;                               // W_kk lower: k <= j
+            int stt = gpb_launch_gemm(g, batch, st);
+            if (stt != GPB_OK) return stt;
         }
-        const int rem = (T - 1 - k) * GPB_NB;
-        if (rem == 0) break;
-        GpbGemm g = gpb_gemm_default();            // panel: A_ik <- A_ik * W_kk^T (in place)
-        g.A = A + (o + GPB_NB) * ld + o; g.lda = ld; g.sA = sA;
-        g.B = W + o * ldw + o; g.ldb = ldw; g.sB = sW;
-        g.C = A + (o + GPB_NB) * ld + o; g.ldc = ld; g.sC = sA;
-        g.M = rem; g.N = GPB_NB; g.K = GPB_NB;
-        g.b_tri = 1;                               // W_kk lower: k <= j
-        int stt = gpb_launch_gemm(g, batch, st);
-        if (stt != GPB_OK) return stt;
-        GpbGemm u = gpb_gemm_default();            // trailing: A_ij -= P_i P_j^T (lower tiles)
-        u.A = g.C; u.lda = ld; u.sA = sA;
-        u.B = g.C; u.ldb = ld; u.sB = sA;
-        u.C = A + (o + GPB_NB) * ld + (o + GPB_NB); u.ldc = ld; u.sC = sA;
-        u.M = rem; u.N = rem; u.K = GPB_NB;
-        u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
-        stt = gpb_launch_gemm(u, batch, st);
-        if (stt != GPB_OK) return stt;
+        const long long t0 = (long long)(k0 + kw) * GPB_NB;
+        const int rem2 = (T - k0 - kw) * GPB_NB;
+        if (rem2 > 0) {                                // trailing: A_ij -= P_i P_j^T (lower tiles)
+            GpbGemm u = gpb_gemm_default();
+            u.A = A + t0 * ld + p0; u.lda = ld; u.sA = sA;
+            u.B = A + t0 * ld + p0; u.ldb = ld; u.sB = sA;
+            u.C = A + t0 * ld + t0; u.ldc = ld; u.sC = sA;
+            u.M = rem2; u.N = rem2; u.K = kw * GPB_NB;
+            u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+            int stt = gpb_launch_gemm(u, batch, st);
+            if (stt != GPB_OK) return stt;
+        }
     }
     return GPB_OK;
 }

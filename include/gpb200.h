@@ -179,6 +179,11 @@ int gpb_periodic_d2K_dpdp(double* out, const double* x1, int64_t n1, const doubl
 int gpb_microbench_fp64(int use_dmma, int iters, double* tflops, double* ms);
 /* number of kernel launches issued by this library since load (bench.py gpu_launches) */
 int64_t gpb_launch_count(void);
+/* Tuning knobs (0 = built-in default; also readable from the environment):
+ *   "eval_streams" (GPB_EVAL_STREAMS) candidate groups evaluated on concurrent streams by gpb_gp_eval
+ *   "gemm_bm"      (GPB_GEMM_BM)      64 (two CTAs per SM) or 128 row tiles in the DMMA GEMM
+ *   "potrf_inner"  (GPB_POTRF_INNER)  128-columns per outer Cholesky panel                    */
+int gpb_set_option(const char* name, int value);
 /* Per-kernel-class device timing: while enabled, each launch group of a class is bracketed
  * by CUDA events on its stream.  Classes: 0 DMMA GEMM, 1 diagonal-block factor, 2 kernel
  * builders / fused mat-vecs, 3 triangular solves, 4 reductions, 5 misc.                 */
