@@ -398,7 +398,7 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     // touches the rest of the matrix -- half (or a quarter) as many passes over the trailing
     // matrix as a plain 128-wide right-looking sweep, each with a longer DMMA main loop.
     int inner = gpb_get_option("potrf_inner");
-    if (inner < 1) inner = 2;
+    if (inner < 1) inner = 4;
     for (int k0 = 0; k0 < T; k0 += inner) {
         const int kw = (T - k0 < inner) ? (T - k0) : inner;
         const long long p0 = (long long)k0 * GPB_NB;
