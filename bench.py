@@ -234,10 +234,15 @@ def run_ours(args):
         _lib.lib.gpb_profile_enable.argtypes = [ctypes.c_int]
         _lib.lib.gpb_profile_enable.restype = None
         _lib.lib.gpb_profile_read.argtypes = [ctypes.c_int, _lib.dp, ctypes.POINTER(ctypes.c_int64)]
+        # per-launch event timing needs the launches serialised on one stream
+        _lib.set_option("eval_streams", 1)
+        ev1 = engine.BatchEvaluator(engine.GAUSSIAN, x, y, max_batch=B)
+        ev1.eval_device(candidates(299, rank, B), want_grad=True)
+        torch.cuda.synchronize()
         _lib.lib.gpb_profile_enable(1)
         psteps = 2
         for k in range(psteps):
-            ev.eval_device(candidates(300 + k, rank, B), want_grad=True)
+            ev1.eval_device(candidates(300 + k, rank, B), want_grad=True)
         torch.cuda.synchronize()
         classes = {}
         for cid, nm in enumerate(["gemm_nt(DMMA)", "potrf_diag", "build+matvec", "trsv", "reduce", "misc"]):
@@ -245,6 +250,8 @@ def run_ours(args):
             _lib.lib.gpb_profile_read(cid, ctypes.byref(m), ctypes.byref(c))
             classes[nm] = {"ms_per_step": m.value / psteps, "launches_per_step": c.value / psteps}
         _lib.lib.gpb_profile_enable(0)
+        _lib.set_option("eval_streams", 0)
+        del ev1
         gemm_ms = classes["gemm_nt(DMMA)"]["ms_per_step"]
         gemm_launches = max(classes["gemm_nt(DMMA)"]["launches_per_step"], 1)
         flops_step = B * float(n) ** 3            # N^3/3 potrf + 2N^3/3 inverse per eval
@@ -257,6 +264,8 @@ def run_ours(args):
                 "peak_source": "measured live: gpb_microbench_fp64 (DMMA.8x8x4 issue rate, 148x8 CTAs); "
                                "MEASURED_PEAKS.json has no fp64 figure",
                 "whole_step_frac": flops_step / (ms / K * 1e-3) / 1e12 / peak,
+                "note": "kernel durations event-timed on one stream (eval_streams=1); the timed region "
+                        "itself runs 4 candidate groups on concurrent streams",
                 "kernel_classes": classes}
         # ---- CPU baseline: the reference's path on this box's host cores (bounded sample) ------
         if world == 1 and not args.no_cpu_baseline:
