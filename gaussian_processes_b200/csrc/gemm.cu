@@ -12,10 +12,12 @@
 //   posterior cov                     Z = Kxox * W^T ;  C = Kxoxo - Z Z^T
 // Triangular operands are exploited at tile granularity through the k-range.
 //
-// Tile 128 x 128 x 16, 256 threads (8 warps as 4 x 2, warp tile 32 x 64 = 4 x 8 DMMA
-// tiles, 64 fp64 accumulators per thread), 4-stage cp.async pipeline (160 KB smem,
-// one CTA per SM).  All extents are multiples of the tile (buffers are padded by the
-// host layer), so there is no edge predication in the main loop.
+// Tile (64 | 128) x 128 x 16 with 32 x 32 warp tiles (4 x 4 DMMA tiles, 32 fp64 accumulators
+// per thread, ~100 registers): the DMMA pipe needs >= 3 resident warps per SM sub-partition to
+// saturate (measured: 1 warp/SMSP 44 %, 2 warps 87 % -- profiles/), so the default 64 x 128 CTA
+// has 8 warps and two CTAs share an SM (4 warps per SMSP).  cp.async multi-stage pipeline.
+// All extents are multiples of the tile (buffers are padded by the host layer), so there is
+// no edge predication in the main loop.
 #include <stdlib.h>
 #include "common.cuh"
 #include "launch.h"
@@ -26,11 +28,11 @@ constexpr int BN = 128, BK = 16;
 constexpr int LDS = BK + 4;   // padded row stride (doubles): conflict-free 8-byte fragment loads
 
 // Two tile shapes share the code:
-//   BM = 128: 256 threads, 4 stages (160 KB smem), one CTA per SM
-//   BM =  64: 128 threads, 3 stages ( 90 KB smem), two CTAs per SM -- the epilogue / prologue of
-//             one CTA overlaps the main loop of the other (short-K trailing updates)
+//   BM = 128: 512 threads (4 x 4 warps), 4 stages (160 KB smem), one CTA per SM
+//   BM =  64: 256 threads (2 x 4 warps), 3 stages ( 90 KB smem), two CTAs per SM -- the epilogue /
+//             prologue of one CTA overlaps the main loop of the other (short-K trailing updates)
 template <int BM> struct TileCfg {
-    static constexpr int THREADS = BM * 2;
+    static constexpr int THREADS = BM * 4;
     static constexpr int STAGES = (BM == 128) ? 4 : 3;
     static constexpr int A_DOUBLES = BM * LDS;
     static constexpr int B_DOUBLES = BN * LDS;
@@ -92,14 +94,14 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
     const int nk = (kend > kbeg) ? (kend - kbeg) / BK : 0;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm = wid >> 1, wn = wid & 1;          // (BM/32) x 2 warps, warp tile 32 x 64
+    const int wm = wid >> 2, wn = wid & 3;          // (BM/32) x 4 warps, warp tile 32 x 32
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[4][8][2];
+    double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 8; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
     // ---- prologue -------------------------------------------------------------
 #pragma unroll
@@ -125,18 +127,18 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
             cp_async_commit();
         }
         const double* as = As + (kt % STAGES) * Cfg::A_DOUBLES + (wm * 32 + g) * LDS + t;
-        const double* bs = Bs + (kt % STAGES) * Cfg::B_DOUBLES + (wn * 64 + g) * LDS + t;
+        const double* bs = Bs + (kt % STAGES) * Cfg::B_DOUBLES + (wn * 32 + g) * LDS + t;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; kk++) {
-            double a[4], b[8];
+            double a[4], b[4];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * LDS + kk * 4];
 #pragma unroll
-            for (int ni = 0; ni < 8; ni++) b[ni] = bs[ni * 8 * LDS + kk * 4];
+            for (int ni = 0; ni < 4; ni++) b[ni] = bs[ni * 8 * LDS + kk * 4];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 8; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
     cp_async_wait<0>();
@@ -150,8 +152,8 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
     for (int mi = 0; mi < 4; mi++) {
         const int r = m0 + wm * 32 + mi * 8 + g;
 #pragma unroll
-        for (int ni = 0; ni < 8; ni++) {
-            const int c = n0 + wn * 64 + ni * 8 + 2 * t;
+        for (int ni = 0; ni < 4; ni++) {
+            const int c = n0 + wn * 32 + ni * 8 + 2 * t;
             double2* dst = reinterpret_cast<double2*>(C + (long long)r * p.ldc + c);
             double v0 = alpha * acc[mi][ni][0], v1 = alpha * acc[mi][ni][1];
             if (beta != 0.0) {
