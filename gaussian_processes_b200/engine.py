@@ -289,6 +289,34 @@ class Engine(object):
         self.gemm(Z, Z, C, mp, mp, self.npad, alpha=-1.0, beta=1.0, lower_only=1, Ct=C)
         return D.to_host(C[:m, :m]).copy()
 
+    def cov_rows(self, xo, lo, hi):
+        """Rows lo:hi of cov(xo) -- the unit of test-point sharding: needs no peer
+        data.  U = K(xo_r, x) Ki, then K(xo_r, xo) - U K(xo, x)^T; 2 N^2 m_r + 2 N M m_r flop."""
+        Ki = self.Ki()
+        m, mb = int(xo.size), int(hi - lo)
+        if mb <= 0 or m == 0:
+            return np.empty((max(mb, 0), m), dtype=DTYPE)
+        mp, mbp = D.roundup(m), D.roundup(mb)
+        dxo = D.to_device(xo)
+        dxr = dxo[lo:hi]
+        Kr = self.build(dxr, mb, self.dx, self.n, mbp, self.npad, 1)[0]
+        U = D.empty(mbp, self.npad)
+        self.gemm(Kr, Ki, U, mbp, self.npad, self.npad)           # Ki symmetric: NT form is K(xo_r,x) Ki
+        Kall = self.build(dxo, m, self.dx, self.n, mp, self.npad, 1)[0]
+        C = self.build(dxr, mb, dxo, m, mbp, mp, 1)[0]
+        self.gemm(U, Kall, C, mbp, mp, self.npad, alpha=-1.0, beta=1.0)
+        return D.to_host(C[:mb, :m]).copy()
+
+    def solve_residual(self):
+        """max |Kxx alpha - y| / max |y| computed on the device with regenerated kernel tiles
+        (size-independent check of the factorisation + solves)."""
+        a = self.alpha()
+        out = D.empty(self.n)
+        call("gpb_kernel_matvec", self.kind, self._theta(), D.ptr(self.dx), self.n, D.ptr(self.dx), self.n, 1,
+             iarr([0]), iarr([0]), darr([1.0]), parr([D.ptr(a)]), 1, parr([D.ptr(out)]), D.stream_ptr())
+        r = out + (self.s ** 2) * a[:self.n] - self.dy[:self.n]
+        return float(r.abs().max().item() / self.dy[:self.n].abs().max().item())
+
     def dm(self, xo):
         """gp_c.dm_dtheta (gp_c.pyx:114-131) with mat-vecs only:
         dm[i] = dK_i(xo,x) alpha - K(xo,x) Ki (dK_i alpha);  s row: -K(xo,x) Ki (2 s alpha)."""

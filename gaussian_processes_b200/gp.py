@@ -325,6 +325,11 @@ class GP(object):
         r"""Predictive covariance (Eq. 2.24 of R&W), :math:`m\times m`."""
         return self._engine().cov(np.asarray(xo, dtype=DTYPE))
 
+    def cov_rows(self, xo, lo, hi):
+        r"""Rows ``lo:hi`` of ``cov(xo)`` (:math:`(hi-lo)\times m`): the shard one GPU owns when
+        test points are partitioned across devices (additive API)."""
+        return self._engine().cov_rows(np.asarray(xo, dtype=DTYPE), int(lo), int(hi))
+
     def dm_dtheta(self, xo):
         r"""Derivative of the predictive mean w.r.t. ``params``: :math:`n_\theta\times m`."""
         return self._engine().dm(np.asarray(xo, dtype=DTYPE))

@@ -1,0 +1,229 @@
+"""BASELINE.json configs C1, C3, C4, C5 on the GPU(s): timing + parity / size-independent checks.
+Single process:  python tests/gpu_configs.py [c1 c3 c4 c5]
+Multi GPU:       torchrun --nproc-per-node G tests/gpu_configs.py c3 c4      (test points / candidates shard)
+Prints one JSON line per config (rank 0) and appends them to gpurun_out/configs.jsonl."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(LOCAL)
+if WORLD > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+import gaussian_processes_b200 as gpb  # noqa: E402
+from gaussian_processes_b200 import device as D  # noqa: E402
+from gaussian_processes_b200.mlii import shard_bounds  # noqa: E402
+from conftest import load_oracle, golden, synth_xy  # noqa: E402
+
+
+def sync():
+    if WORLD > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def maxtime(t):
+    v = torch.tensor([t], dtype=torch.float64, device="cuda")
+    if WORLD > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    return float(v.item())
+
+
+def emit(d):
+    d["n_gpus"] = WORLD
+    if RANK == 0:
+        print(json.dumps(d), flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "a") as f:
+            f.write(json.dumps(d) + "\n")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def c1():
+    """N=50, Gaussian(1, 0.2), s=0: log_lh + dloglh_dtheta + mean/cov at 100 test points."""
+    g = golden("gp_c1")
+    x, y, xo = g["x"], g["y"], g["xo"]
+    gp = gpb.GP(gpb.GaussianKernel(1.0, 0.2), x, y, s=0)
+    errs = dict(log_lh=rel(gp.log_lh, g["log_lh"]), dloglh=rel(gp.dloglh_dtheta, g["dloglh_dtheta"]),
+                mean=rel(gp.mean(xo), g["mean"]), cov=rel(gp.cov(xo), g["cov"]))
+    reps = 50
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(reps):
+        gp.set_param("w", 0.2 + 1e-6 * (k + 1))
+        gp.log_lh, gp.dloglh_dtheta, gp.mean(xo), gp.cov(xo)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    emit(dict(config="C1", metric="bundles/s (log_lh+grad+mean+cov, N=50, M=100)", value=1 / dt,
+              ms_per_bundle=dt * 1e3, parity_vs_reference=errs))
+
+
+def c3():
+    """Periodic N=8192: Kxx + jacobian/hessian builds, posterior mean/cov at M=16384, test points sharded."""
+    n, m = 8192, 16384
+    x, y = synth_xy(n, 0)
+    xo = np.linspace(-2 * np.pi, 2 * np.pi, m)
+    gp = gpb.GP(gpb.PeriodicKernel(1.0, 1.0, 1.0), x, y, s=1.0)
+    e = gp._engine()
+    out = dict(config="C3", n=n, m=m)
+    # builders on the device (HBM-write roofline): K, jacobian (3 slices), hessian (9 slices), all 13 fused
+    for name, mask, ns in (("K", 0x1, 1), ("jacobian", 0xE, 3), ("hessian", 0x1FF0, 9), ("all13", 0x1FFF, 13)):
+        buf = D.empty(ns, e.npad, e.npad)
+        e.build(e.dx, n, e.dx, n, e.npad, e.npad, mask, out=buf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e.build(e.dx, n, e.dx, n, e.npad, e.npad, mask, out=buf)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out["build_%s_ms" % name] = ms
+        out["build_%s_GBps" % name] = ns * n * n * 8 / ms / 1e6
+        del buf
+    # factorisation + inverse (every rank, redundantly -- SURVEY 8e)
+    sync()
+    t0 = time.perf_counter()
+    llh = gp.log_lh
+    e.Ki()
+    torch.cuda.synchronize()
+    out["factor_inverse_ms"] = (time.perf_counter() - t0) * 1e3
+    out["log_lh"] = float(llh)
+    out["solve_residual"] = e.solve_residual()
+    # sharded posterior: rank r owns test points [lo, hi)
+    lo, hi = shard_bounds(m, WORLD, RANK)
+    gp.mean(xo[lo:hi]); gp.cov_rows(xo[:256], 0, 128)      # warm
+    sync()
+    t0 = time.perf_counter()
+    mean_r = gp.mean(xo[lo:hi])
+    torch.cuda.synchronize()
+    tm = maxtime(time.perf_counter() - t0)
+    sync()
+    t0 = time.perf_counter()
+    cov_r = gp.cov_rows(xo, lo, hi)
+    torch.cuda.synchronize()
+    tc = maxtime(time.perf_counter() - t0)
+    out.update(mean_test_pts_per_s=m / tm, cov_test_pts_per_s=m / tc, mean_ms=tm * 1e3, cov_rows_ms=tc * 1e3,
+               cov_includes="D2H of the [m_r, M] row block")
+    # checks: symmetric block, agreement with the Z Z^T path on a sub-block, oracle on a small sub-problem
+    if RANK == 0:
+        sub = gp.cov(xo[lo:lo + 300])
+        out["cov_rows_vs_cov_block"] = rel(cov_r[:300, lo:lo + 300], sub)
+        oracle = load_oracle()
+        ns = 1024
+        xs, ys = x[::8][:ns], y[::8][:ns]
+        gps = gpb.GP(gpb.PeriodicKernel(1.0, 1.0, 1.0), xs, ys, s=1.0)
+        o = oracle.OracleGP(oracle.PERIODIC, (1.0, 1.0, 1.0), xs, ys, 1.0)
+        out["parity_subproblem_n1024"] = dict(mean=rel(gps.mean(xo[:200]), o.mean(xo[:200])),
+                                              cov_rows=rel(gps.cov_rows(xo[:200], 50, 120), o.cov(xo[:200])[50:120]),
+                                              log_lh=rel(gps.log_lh, o.log_lh), dloglh=rel(gps.dloglh_dtheta, o.dloglh_dtheta))
+    emit(out)
+
+
+def c4():
+    """Batched fit_MLII: 4096 restarts x N=1024 Gaussian, candidates sharded, NCCL argmax gather."""
+    n, B = 1024, 4096
+    x, y = synth_xy(n, 0)
+    rng = np.random.RandomState(4)
+    cand = np.stack([rng.uniform(0.5, 2, B), rng.uniform(np.pi / 32, np.pi / 2, B), rng.uniform(0.75, 1.5, B)], axis=1)
+    gp = gpb.GP(gpb.GaussianKernel(1.0, 1.0), x, y, s=1.0)
+    gp.fit_MLII(cand[:64 * WORLD], set_params=False)          # warm (workspace, NCCL)
+    sync()
+    t0 = time.perf_counter()
+    res = gp.fit_MLII(cand, set_params=False)
+    torch.cuda.synchronize()
+    dt = maxtime(time.perf_counter() - t0)
+    out = dict(config="C4", n=n, restarts=B, value=B / dt, metric="candidate evals/s (log_lh+grad), whole job",
+               seconds=dt, best_index=res.best_index, best_log_lh=float(res.best_log_lh))
+    if RANK == 0:
+        oracle = load_oracle()
+        idx = [res.best_index, 0, 1, B - 1]
+        errs = []
+        for i in idx:
+            o = oracle.OracleGP(oracle.GAUSSIAN, cand[i, :2], x, y, cand[i, 2])
+            errs.append((rel(res.log_lh[i], o.log_lh), rel(res.dloglh_dtheta[i], o.dloglh_dtheta)))
+        out["parity_spot_checks"] = errs
+        out["argmax_consistent"] = bool(res.best_index == int(np.argmax(np.where(np.isnan(res.log_lh), -np.inf, res.log_lh))))
+    emit(out)
+
+
+def c5():
+    """N=32768 fp64 (8.6 GB Kxx): single-GPU Cholesky + cho_solve + full posterior cov at M=8192."""
+    if RANK != 0:
+        return
+    n, m = 32768, 8192
+    x, y = synth_xy(n, 0)
+    xo = np.linspace(-2 * np.pi, 2 * np.pi, m)
+    gp = gpb.GP(gpb.GaussianKernel(1.0, 0.5), x, y, s=1.0)
+    e = gp._engine()
+    out = dict(config="C5", n=n, m=m)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    info = e.factor()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e.alpha()
+    llh = gp.log_lh
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    out.update(info=info, potrf_ms=(t1 - t0) * 1e3, potrf_tflops=n ** 3 / 3 / (t1 - t0) / 1e12,
+               solve_loglh_ms=(t2 - t1) * 1e3, log_lh=float(llh), solve_residual=e.solve_residual())
+    t0 = time.perf_counter()
+    cov = gp.cov(xo)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter() - t0
+    out.update(cov_ms=t3 * 1e3, cov_test_pts_per_s=m / t3, cov_includes="trtri + Z=Kxox L^-T + Kxoxo - Z Z^T + D2H of 0.5 GB")
+    t0 = time.perf_counter()
+    mean = gp.mean(xo)
+    torch.cuda.synchronize()
+    out["mean_ms"] = (time.perf_counter() - t0) * 1e3
+    # independent check of a few covariance entries: cho_solve path (substitution) instead of L^-1
+    idx = [0, 1234, m - 1]
+    kv = gpb.GaussianKernel(1.0, 0.5)(x, xo[idx])                    # [n, 3]
+    worst = 0.0
+    for c, j in enumerate(idx):
+        g2 = gpb.GP(gpb.GaussianKernel(1.0, 0.5), x, kv[:, c].copy(), s=1.0)
+        g2._dev = gp._dev                                             # reuse the factor; only y differs
+        eng = gp._engine()
+        a_saved, y_saved = eng._c.pop("alpha", None), eng.dy
+        eng.dy = D.to_device(kv[:, c], pad_to=eng.npad)
+        sol = D.to_host(eng.alpha()[:n]).copy()
+        eng._c.pop("alpha", None)
+        eng.dy = y_saved
+        if a_saved is not None:
+            eng._c["alpha"] = a_saved
+        ref_col = gpb.GaussianKernel(1.0, 0.5)(xo, xo[j:j + 1])[:, 0] - kv.T[c] @ sol * 0 - (gpb.GaussianKernel(1.0, 0.5)(xo, x) @ sol)
+        worst = max(worst, rel(cov[:, j], ref_col))
+    out["cov_columns_vs_cho_solve_path"] = worst
+    out["cov_symmetry"] = float(np.max(np.abs(cov - cov.T)))
+    out["cov_diag_min"] = float(np.min(np.diag(cov)))
+    out["peak_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
+    emit(out)
+
+
+if __name__ == "__main__":
+    which = [a for a in sys.argv[1:] if a in ("c1", "c3", "c4", "c5")] or ["c1", "c3", "c4", "c5"]
+    for w in which:
+        try:
+            globals()[w]()
+        except Exception as exc:
+            import traceback
+            traceback.print_exc()
+            emit(dict(config=w.upper(), error=repr(exc)))
+    if WORLD > 1:
+        dist.barrier()
+        dist.destroy_process_group()
