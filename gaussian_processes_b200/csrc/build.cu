@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const GradArgs a) {
     unsigned need = 0;
     for (int q = 0; q < a.nsl; q++) need |= 1u << a.uq[q];
 
+    // Ki and every slice S are symmetric (x1 == x2): visit only c <= r and weight the strict
+    // lower part twice -- half the exp / sincos evaluations and half the Ki traffic.
     double t0[GPB_RED_MAXS], t1[GPB_RED_MAXS], tr = 0, aa = 0;
 #pragma unroll
     for (int q = 0; q < GPB_RED_MAXS; q++) t0[q] = t1[q] = 0.0;
@@ -267,10 +269,11 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const GradArgs a) {
         double q0[GPB_RED_MAXS];
 #pragma unroll
         for (int q = 0; q < GPB_RED_MAXS; q++) q0[q] = 0.0;
-        for (long long c = lane; c < a.n; c += 32) {
+        for (long long c = lane; c <= r; c += 32) {
             double u[10];
             gpb_eval_unique<KIND>(sP, xi - a.x[c], need, u);
-            const double k = row[c], ac = al[c];
+            const double wgt = (c < r) ? 2.0 : 1.0;
+            const double k = wgt * row[c], ac = wgt * al[c];
 #pragma unroll
             for (int q = 0; q < GPB_RED_MAXS; q++) {
                 if (q < a.nsl) {
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const GradArgs a) {
                     t1[q] += v * k;
                 }
             }
-            if (c == r) tr += k;
+            if (c == r) tr += row[c];
         }
 #pragma unroll
         for (int q = 0; q < GPB_RED_MAXS; q++) t0[q] += ar * q0[q];

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
     // ---- tile coordinates -------------------------------------------------
     int ti, tj;
     bool diag_tile = false;
+    int diag_sub = -1;          // BM = 64: which half (0 = rows 0-63, 1 = rows 64-127) of a diagonal 128-block
     if (p.lower_only) {
         // blockIdx.x enumerates the tiles that touch the lower triangle, by 128-row groups:
         // group q holds (128/BM) row tiles with q+1 column tiles each.
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
         tj = t - i * (i + 1) / 2;
         ti = i * RPG + sub;
         diag_tile = (tj == i);
+        if (diag_tile && RPG == 2) diag_sub = sub;
     } else {
         // longest k-range first: for a lower-triangular A the work grows with the row
         ti = (p.a_tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
@@ -96,6 +98,11 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm = wid >> 2, wn = wid & 3;          // (BM/32) x 4 warps, warp tile 32 x 32
     const int g = lane >> 2, t = lane & 3;
+
+    // upper-right 64x64 quadrant of a diagonal block: strictly above the diagonal, never needed
+    // (its values are the mirror of the lower-left quadrant).  Those warps skip the DMMA work and
+    // leave the pipe to the co-resident CTA.
+    const bool skip_mma = (diag_sub == 0) && (wn >= 2);
 
     double acc[4][4][2];
 #pragma unroll
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
         }
         const double* as = As + (kt % STAGES) * Cfg::A_DOUBLES + (wm * 32 + g) * LDS + t;
         const double* bs = Bs + (kt % STAGES) * Cfg::B_DOUBLES + (wn * 32 + g) * LDS + t;
+        if (skip_mma) continue;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; kk++) {
             double a[4], b[4];
@@ -146,7 +154,11 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
     // ---- epilogue -----------------------------------------------------------------
     double* C = p.C + bz * p.sC + bt * p.tC;
     double* Ct = p.Ct ? p.Ct + bz * p.sCt + bt * p.tCt : nullptr;
-    const bool mirror = (Ct != nullptr) && !(p.lower_only && diag_tile && Ct == C);
+    // mirrored store: off-diagonal tiles always; inside a diagonal block only the lower-left
+    // quadrant (second half-tile, columns 0-63) is mirrored into the skipped upper-right one.
+    bool mirror = (Ct != nullptr) && !(p.lower_only && diag_tile && Ct == C);
+    if (Ct != nullptr && diag_sub == 1 && wn < 2) mirror = true;
+    if (skip_mma) return;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
