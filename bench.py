@@ -258,7 +258,11 @@ def run_ours(args):
         achieved = flops_step / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA.8x8x4)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the gemm_nt launches of one step, from
+                # the ncu pass committed as profiles/r01_launches_one_step_b16_dram.csv
+                # (18.60 GB over 73 launches at B=16 -> 15.93 MB per launch per candidate)
+                "traffic": 15.93e6 * B,
+                "traffic_source": "ncu dram bytes, profiles/r01_launches_one_step_b16_dram.csv (per launch, scaled by B/16)",
                 "algorithmic_flops_per_launch": flops_step / gemm_launches,
                 "avg_launch_ms": gemm_ms / gemm_launches, "launches_per_step": gemm_launches,
                 "peak_source": "measured live: gpb_microbench_fp64 (DMMA.8x8x4 issue rate, 148x8 CTAs); "
@@ -286,6 +290,28 @@ def run_ours(args):
             cpu["parity_rel_err_log_lh"] = abs(chk[0][0] - cl) / abs(cl)
             cpu["parity_rel_err_grad"] = float(np.max(np.abs(chk[1][0] - cg)) / np.max(np.abs(cg)))
 
+    # ---- second half of BASELINE's metric: posterior mean / cov test points per second ----------
+    posterior = None
+    if rank == 0 and not args.no_posterior:
+        gpp = gpb.GP(gpb.GaussianKernel(1.0, 0.5), x, y, s=1.0)
+        m_mean, m_cov = 16384, 4096
+        xo_mean = np.linspace(-2 * np.pi, 2 * np.pi, m_mean)
+        xo_cov = np.linspace(-2 * np.pi, 2 * np.pi, m_cov)
+        gpp.mean(xo_mean[:256]); gpp.cov(xo_cov[:256])          # fit once: factor, solves, L^-1 (cached)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(5):
+            gpp.mean(xo_mean + 1e-9 * k)
+        t_mean = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        for k in range(3):
+            gpp.cov(xo_cov + 1e-9 * k)
+        t_cov = (time.perf_counter() - t0) / 3
+        posterior = {"mean_test_pts_per_s": m_mean / t_mean, "cov_test_pts_per_s": m_cov / t_cov,
+                     "m_mean": m_mean, "m_cov": m_cov, "n": n,
+                     "note": "public API on a fitted GP (factor + L^-1 cached), host xo in, numpy out "
+                             "(cov includes the D2H of the M x M result)"}
+
     if rank == 0:
         line = {
             "metric": "log_lh+dloglh_dtheta evals/sec at N=%d fp64" % n,
@@ -306,6 +332,8 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if posterior is not None:
+            line["posterior"] = posterior
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -318,9 +346,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="candidates per GPU per step")
+    ap.add_argument("--batch", type=int, default=16, help="candidates per GPU per step")
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-posterior", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
