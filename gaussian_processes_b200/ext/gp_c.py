@@ -140,11 +140,11 @@ def d2lh_dtheta2(y, Ki, Kj, Kh, Kiy, s, lh, dlh, d2lh):
     sc = _Scratch(n)
     res = np.empty((nth, nth))
     KiT_y = _gemv(dKiT, npad, npad, npad, dy)                                      # (y^T Ki)^T
-    slots = {}
+    eye = _eye(npad)
     for i in range(nth):
         dKiT_i = dK[i].t().contiguous()
-        slots[("r0", i)] = sc.quadform(KiT_y, dK[i], npad, dKiy, n)                # y^T Ki dK_i Kiy
-        slots[("r1", i)] = sc.trace_prod(dKi, dK[i], npad, n)                      # tr(Ki dK_i)
+        sc.quadform(KiT_y, dK[i], npad, dKiy, n)                                   # y^T Ki dK_i Kiy
+        sc.trace_prod(dKi, dK[i], npad, n)                                         # tr(Ki dK_i)
         for j in range(nth):
             G = _gemm(dKi_l[j], dKiT_i, D.empty(npad, npad), npad, npad, npad)     # dKi_j dK_i
             if i < n_p and j < n_p:
@@ -155,12 +155,12 @@ def d2lh_dtheta2(y, Ki, Kj, Kh, Kiy, s, lh, dlh, d2lh):
             else:
                 d2k = D.zeros(npad, npad)
             sc2 = _Scratch(n)
-            a = sc2.quadform(dy, G, npad, dKiy, n)                                 # t1a
-            b = sc2.quadform(dKiy, d2k, npad, dKiy, n)                             # t1b
+            sc2.quadform(dy, G, npad, dKiy, n)                                     # t1a
+            sc2.quadform(dKiy, d2k, npad, dKiy, n)                                 # t1b
             w = _gemv(dKi_l[j], npad, npad, npad, dy)                              # dKi_j y
-            c = sc2.quadform(dKiy, dK[i], npad, w, n)                              # t1c
-            tG = sc2.trace_prod(G, _eye(npad), npad, n)
-            tK = sc2.trace_prod(dKi, d2k, npad, n)
+            sc2.quadform(dKiy, dK[i], npad, w, n)                                  # t1c
+            sc2.trace_prod(G, eye, npad, n)                                        # tr(dKi_j dK_i)
+            sc2.trace_prod(dKi, d2k, npad, n)                                      # tr(Ki d2k)
             v = sc2.values()
             res[i, j] = v[0] + v[1] + v[2] - (v[3] + v[4])
     v = sc.values()

@@ -268,3 +268,57 @@ def test_periodic_posterior_sharded_blocks(oracle):
     assert_parity(gp.mean(xo[lo:hi]), mean[lo:hi], 1e-13)
     assert_parity(gp.cov(xo[lo:hi]), cov[lo:hi, lo:hi], 1e-12)
     assert_parity(gp.Kxx_J, o.Kxx_J, 1e-13)
+
+
+# ------------------------------------------------------------------ newer surface
+def test_cov_rows_matches_cov(oracle):
+    """Row blocks of the predictive covariance (the unit of test-point sharding) against the
+    oracle's full covariance, including ragged block boundaries."""
+    x, y = synth_xy(300, 5)
+    xo = np.linspace(-6, 6, 211)
+    gp = GP(GaussianKernel(1.0, 0.5), x, y, s=1.0)
+    ref = oracle.OracleGP(oracle.GAUSSIAN, (1.0, 0.5), x, y, 1.0).cov(xo)
+    for lo, hi in ((0, 211), (0, 1), (17, 150), (130, 211)):
+        assert_parity(gp.cov_rows(xo, lo, hi), ref[lo:hi], RTOL, "rows %d:%d" % (lo, hi))
+    assert gp.cov_rows(xo, 5, 5).shape == (0, 211)
+
+
+def test_batch_eval_chunking_and_knobs():
+    """Chunked evaluation (workspace smaller than the batch) and every tuning knob give the same
+    numbers: the knobs change scheduling, never arithmetic order within a candidate."""
+    from gaussian_processes_b200 import _lib, engine
+    x, y = synth_xy(700, 9)
+    rng = np.random.RandomState(2)
+    th = np.stack([rng.uniform(0.5, 2, 11), rng.uniform(0.2, 1.0, 11), rng.uniform(0.75, 1.5, 11)], axis=1)
+    base = engine.BatchEvaluator(engine.GAUSSIAN, x, y).eval(th)
+    small = engine.BatchEvaluator(engine.GAUSSIAN, x, y, max_batch=3).eval(th)
+    assert np.array_equal(base[0], small[0]) and np.array_equal(base[1], small[1])
+    try:
+        for name, vals in (("eval_streams", (1, 2)), ("gemm_bm", (128, 64)), ("potrf_inner", (1, 2))):
+            for v in vals:
+                _lib.set_option(name, v)
+                got = engine.BatchEvaluator(engine.GAUSSIAN, x, y).eval(th)
+                assert_parity(got[0], base[0], 1e-13, "%s=%d llh" % (name, v))
+                assert_parity(got[1], base[1], 1e-11, "%s=%d grad" % (name, v))
+                _lib.set_option(name, 0)
+    finally:
+        for name in ("eval_streams", "gemm_bm", "potrf_inner"):
+            _lib.set_option(name, 0)
+    with pytest.raises(_lib.GpbError):
+        _lib.set_option("no_such_knob", 1)
+
+
+def test_clamp_candidates_in_batch(oracle):
+    """Reference-suite noise range s ~ U(0, 0.5) (tests/util.py:24-25) at N=1024: most candidates hit
+    the logdet < MIN clamp; batched rows must reproduce -inf with finite gradients."""
+    x, y = synth_xy(1024, 0)
+    rng = np.random.RandomState(8)
+    th = np.stack([rng.uniform(0.5, 2, 6), rng.uniform(0.3, 1.0, 6), rng.uniform(0.05, 0.5, 6)], axis=1)
+    gp = GP(GaussianKernel(1.0, 0.5), x, y, s=1.0)
+    llh, grad = gp.batch_eval(th)
+    for b in range(3):
+        o = oracle.OracleGP(oracle.GAUSSIAN, th[b, :2], x, y, th[b, 2])
+        assert (llh[b] == -np.inf) == (o.log_lh == -np.inf)
+        if np.isfinite(o.log_lh):
+            assert_parity(llh[b], o.log_lh, 1e-8)
+    assert (llh == -np.inf).any() and np.isfinite(grad).all()
