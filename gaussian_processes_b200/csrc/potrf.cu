@@ -20,33 +20,46 @@ namespace {
 
 // ===========================================================================
 // diagonal-block kernel: one CTA factors and inverts one 128 x 128 block held in
-// shared memory as ten 32 x 32 sub-blocks (lower block-triangle) + ten for W.
+// shared memory as ten 32 x 32 sub-blocks (lower block-triangle).
+//
+// Resource shape is part of the design: 138.5 KB of shared memory and <= 128 registers
+// x 256 threads, so that a diagonal-block CTA can be placed on an SM next to ONE resident
+// 64x128 GEMM CTA (92 KB, half the register file) of another candidate group instead of
+// waiting for a completely idle SM -- this is what lets the serial part of one group's
+// factorisation overlap the trailing updates of the others.
+//
+// Per 32-column step bb:
+//   P1  warp 0        Cholesky of the 32x32 diagonal sub-block in registers (lane = row,
+//                     pivots / columns by warp shuffle, rsqrt on the critical path)
+//   P2  warp 0        its inverse (lane = column, forward substitution)      } concurrently
+//   P3  warps 1..3    rows below: X = A L_bb^-T by substitution, lane = row   }
+//   P4  all warps     trailing update inside the tile on DMMA
+// then W = L^-1 is completed block by block (DMMA), results streamed to W / V = W^T.
 // ===========================================================================
 constexpr int SB = 32;            // sub-block edge
 constexpr int SLD = 36;           // padded stride: 36 = 4 (mod 16) -> conflict-free DMMA fragment loads
 constexpr int SBSZ = SB * SLD;
 constexpr int NBLK = 10;
-constexpr int DLD = 33;           // odd stride for the lane-per-row accesses of the 32x32 factor
-constexpr int DIAG_SMEM = (2 * NBLK * SBSZ + SB * DLD + SB) * 8;
+constexpr int DLD = 33;           // odd stride for lane-per-row accesses
+constexpr int DIAG_SMEM = ((NBLK + 4 + 1) * SBSZ + SB) * 8;     // L blocks, diagonal inverses, staging, 1/diag
 
 __device__ __forceinline__ int blk(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ldw, long long sW,
                   double* V, long long ldv, long long sV, int* info, int col0) {
     extern __shared__ __align__(16) double sm[];
-    double* Lb = sm;
-    double* Wb = sm + NBLK * SBSZ;
-    double* D = Wb + NBLK * SBSZ;
-    double* invd = D + SB * DLD;
+    double* Lb = sm;                          // 10 lower sub-blocks of the tile
+    double* Wd = sm + NBLK * SBSZ;            // inverses of the 4 diagonal sub-blocks
+    double* D = Wd + 4 * SBSZ;                // staging block (stride 33 in P1-P3, stride 36 later)
+    double* invd = D + SBSZ;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
     A += (long long)blockIdx.x * sA;
     W += (long long)blockIdx.x * sW;
     if (V) V += (long long)blockIdx.x * sV;
     info += blockIdx.x;
 
-    // ---- load the lower block-triangle -----------------------------------------
-    // (all copies are issued before the first wait: one memory round trip, not forty)
+    // ---- load the lower block-triangle (all copies in flight before the single wait) -------
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((ld & 1) == 0);
     for (int bi = 0; bi < 4; bi++)
         for (int bj = 0; bj <= bi; bj++) {
@@ -68,8 +81,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     __syncthreads();
 
     for (int bb = 0; bb < 4; bb++) {
-        // ---- phase 1+2 (warp 0): Cholesky of the 32x32 diagonal sub-block in registers
-        //      (lane i owns row i; pivots/columns travel by warp shuffle), then its inverse.
+        // ---- P1 (warp 0): 32x32 Cholesky in registers ------------------------------------
         if (wid == 0) {
             double* Ld = Lb + blk(bb, bb) * SBSZ;
             for (int r = 0; r < SB; r++) D[r * DLD + lane] = Ld[r * SLD + lane];
@@ -102,7 +114,12 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             if (fail && lane == 0 && *info == 0) *info = col0 + bb * SB + fail;
             __syncwarp();
             for (int r = 0; r < SB; r++) Ld[r * SLD + lane] = D[r * DLD + lane];
-            // inverse: lane c solves L w = e_c by forward substitution (L rows broadcast from D)
+        }
+        __syncthreads();
+
+        const int nbelow = 3 - bb;
+        if (wid == 0) {
+            // ---- P2 (warp 0): inverse of L_bb, lane c solves L w = e_c (rows of L broadcast) ----
             double w[SB];
 #pragma unroll
             for (int r = 0; r < SB; r++) {
@@ -115,37 +132,40 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
                 if (r & 1) s0 = fma(D[r * DLD + r - 1], w[r - 1], s0);
                 w[r] = (((r == lane) ? 1.0 : 0.0) - (s0 + s1)) * invd[r];
             }
-            double* Wd = Wb + blk(bb, bb) * SBSZ;
+            double* Wo = Wd + bb * SBSZ;
 #pragma unroll
-            for (int r = 0; r < SB; r++) Wd[r * SLD + lane] = w[r];
-        }
-        __syncthreads();
-
-        const int nbelow = 3 - bb;
-        // ---- phase 3: L_ib = A_ib * W_bb^T for the sub-blocks below (warp owns 8 rows) ----
-        for (int item = wid; item < nbelow * 4; item += 8) {
-            const int bi = bb + 1 + (item >> 2), rt = item & 3;
-            double* Ab = Lb + blk(bi, bb) * SBSZ + (rt * 8 + g) * SLD;
-            const double* Wd = Wb + blk(bb, bb) * SBSZ + g * SLD + t;
-            double acc[4][2];
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++) acc[ni][0] = acc[ni][1] = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) {
-                const double a = Ab[kk * 4 + t];
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[ni][0], acc[ni][1], a, Wd[ni * 8 * SLD + kk * 4]);
-            }
+            for (int r = 0; r < SB; r++) Wo[r * SLD + lane] = w[r];
+        } else if (wid <= nbelow) {
+            // ---- P3 (warps 1..nbelow): sub-block (bb+wid, bb): X = A L_bb^-T, lane = row.
+            //      The still unused inverse slot of that block row is the warp's private staging
+            //      area, so every shared-memory access below is conflict-free.
+            const int bi = bb + wid;
+            double* Ab = Lb + blk(bi, bb) * SBSZ;
+            double* St = Wd + bi * SBSZ;
+            for (int r = 0; r < SB; r++) St[r * DLD + lane] = Ab[r * SLD + lane];
             __syncwarp();
+            double xr[SB];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
-                Ab[ni * 8 + 2 * t] = acc[ni][0];
-                Ab[ni * 8 + 2 * t + 1] = acc[ni][1];
+            for (int c = 0; c < SB; c++) xr[c] = St[lane * DLD + c];
+#pragma unroll
+            for (int c = 0; c < SB; c++) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int l = 0; l + 1 < c; l += 2) {
+                    s0 = fma(xr[l], D[c * DLD + l], s0);
+                    s1 = fma(xr[l + 1], D[c * DLD + l + 1], s1);
+                }
+                if (c & 1) s0 = fma(xr[c - 1], D[c * DLD + c - 1], s0);
+                xr[c] = (xr[c] - (s0 + s1)) * invd[c];
             }
+#pragma unroll
+            for (int c = 0; c < SB; c++) St[lane * DLD + c] = xr[c];
+            __syncwarp();
+            for (int r = 0; r < SB; r++) Ab[r * SLD + lane] = St[r * DLD + lane];
         }
         __syncthreads();
 
-        // ---- phase 4: trailing update A_ij -= L_ib L_jb^T, bb < j <= i ----------------------
+        // ---- P4: trailing update A_ij -= L_ib L_jb^T, bb < j <= i, on DMMA -------------------
         const int npairs = nbelow * (nbelow + 1) / 2;
         for (int item = wid; item < npairs * 16; item += 8) {
             const int pr = item >> 4, rt = (item >> 2) & 3, ct = item & 3;
@@ -165,8 +185,50 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
         __syncthreads();
     }
 
-    // ---- phase 5: off-diagonal sub-blocks of W = L^-1, by block distance d ------------
-    //      W_ij = -W_ii * sum_{k=j}^{i-1} L_ik W_kj
+    // ---- L is final: stream it out (zeros above the diagonal), which also frees the four
+    //      diagonal L slots as scratch for the inverse ------------------------------------------
+    for (int bi = 0; bi < 4; bi++)
+        for (int bj = 0; bj < 4; bj++) {
+            const bool low = bi >= bj;
+            const double* ls = Lb + (low ? blk(bi, bj) : 0) * SBSZ;
+            for (int e = tid; e < SB * SB; e += 256) {
+                const int r = e >> 5, c = e & 31;
+                A[(long long)(bi * SB + r) * ld + bj * SB + c] = low ? ls[r * SLD + c] : 0.0;
+            }
+        }
+    // diagonal sub-blocks of W / V and the structural zeros of both
+    for (int bi = 0; bi < 4; bi++)
+        for (int bj = 0; bj < 4; bj++) {
+            if (bi > bj) {                       // W strictly-lower blocks come from phase 5; V's are zero
+                if (V)
+                    for (int e = tid; e < SB * SB; e += 256)
+                        V[(long long)(bi * SB + (e >> 5)) * ldv + bj * SB + (e & 31)] = 0.0;
+                continue;
+            }
+            const double* ws = Wd + bi * SBSZ;
+            for (int e = tid; e < SB * SB; e += 256) {
+                const int r = e >> 5, c = e & 31;
+                const long long gr = bi * SB + r, gc = bj * SB + c;
+                if (bi == bj) {
+                    W[gr * ldw + gc] = ws[r * SLD + c];
+                    if (V) V[gr * ldv + gc] = ws[c * SLD + r];
+                } else {
+                    W[gr * ldw + gc] = 0.0;      // W strictly-upper blocks; V's come from phase 5
+                }
+            }
+        }
+    __syncthreads();
+
+    // ---- P5: off-diagonal sub-blocks of W = L^-1 by block distance d:
+    //      W_ij = -W_ii * S,  S = sum_{k=j}^{i-1} L_ik W_kj
+    //      slots: S(i,j) -> freed diagonal slot j;  W_10 -> diagonal slot 3, W_21 -> staging block,
+    //      W_20 -> diagonal slot 2 (the only results that later rounds read back).
+    auto wsrc = [&](int k, int j) -> const double* {
+        if (k == j) return Wd + k * SBSZ;
+        if (k == 1) return Lb + blk(3, 3) * SBSZ;              // W_10
+        if (j == 1) return D;                                  // W_21
+        return Lb + blk(2, 2) * SBSZ;                          // W_20
+    };
     for (int d = 1; d < 4; d++) {
         const int nj = 4 - d;
         for (int item = wid; item < nj * 16; item += 8) {
@@ -174,55 +236,40 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             double c0 = 0.0, c1 = 0.0;
             for (int k = j; k < i; k++) {
                 const double* Ap = Lb + blk(i, k) * SBSZ + (rt * 8 + g) * SLD + t;
-                const double* Bp = Wb + blk(k, j) * SBSZ + t * SLD + ct * 8 + g;
+                const double* Bp = wsrc(k, j) + t * SLD + ct * 8 + g;
 #pragma unroll
                 for (int kk = 0; kk < 8; kk++) dmma884(c0, c1, Ap[kk * 4], Bp[kk * 4 * SLD]);
             }
-            double* Sb = Wb + blk(i, j) * SBSZ + (rt * 8 + g) * SLD + ct * 8 + 2 * t;
+            double* Sb = Lb + blk(j, j) * SBSZ + (rt * 8 + g) * SLD + ct * 8 + 2 * t;
             Sb[0] = c0;
             Sb[1] = c1;
         }
         __syncthreads();
-        for (int item = wid; item < nj * 4; item += 8) {      // warp owns a column tile: in-place safe
-            const int j = item >> 2, ct = item & 3, i = j + d;
-            double acc[4][2];
+        for (int item = wid; item < nj * 16; item += 8) {
+            const int j = item >> 4, rt = (item >> 2) & 3, ct = item & 3, i = j + d;
+            double c0 = 0.0, c1 = 0.0;
+            const double* Wi = Wd + i * SBSZ + (rt * 8 + g) * SLD + t;
+            const double* Sp = Lb + blk(j, j) * SBSZ + t * SLD + ct * 8 + g;
 #pragma unroll
-            for (int rt = 0; rt < 4; rt++) acc[rt][0] = acc[rt][1] = 0.0;
-            const double* Sp = Wb + blk(i, j) * SBSZ + t * SLD + ct * 8 + g;
-            const double* Wi = Wb + blk(i, i) * SBSZ + g * SLD + t;
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) {
-                const double b = Sp[kk * 4 * SLD];
-#pragma unroll
-                for (int rt = 0; rt < 4; rt++) dmma884(acc[rt][0], acc[rt][1], -Wi[rt * 8 * SLD + kk * 4], b);
+            for (int kk = 0; kk < 8; kk++) dmma884(c0, c1, -Wi[kk * 4], Sp[kk * 4 * SLD]);
+            double* keep = nullptr;
+            if (i == 1) keep = Lb + blk(3, 3) * SBSZ;           // W_10
+            else if (i == 2 && j == 1) keep = D;                // W_21
+            else if (i == 2 && j == 0) keep = Lb + blk(2, 2) * SBSZ;   // W_20
+            const int r = rt * 8 + g, c = ct * 8 + 2 * t;
+            if (keep) {
+                keep[r * SLD + c] = c0;
+                keep[r * SLD + c + 1] = c1;
             }
-            __syncwarp();
-            double* Ob = Wb + blk(i, j) * SBSZ + g * SLD + ct * 8 + 2 * t;
-#pragma unroll
-            for (int rt = 0; rt < 4; rt++) {
-                Ob[rt * 8 * SLD] = acc[rt][0];
-                Ob[rt * 8 * SLD + 1] = acc[rt][1];
+            const long long gr = i * SB + r, gc = j * SB + c;
+            *reinterpret_cast<double2*>(W + gr * ldw + gc) = make_double2(c0, c1);
+            if (V) {
+                V[gc * ldv + gr] = c0;
+                V[(gc + 1) * ldv + gr] = c1;
             }
         }
         __syncthreads();
     }
-
-    // ---- store L (lower, zero above), W (lower) and V = W^T (upper) ----------------------
-    for (int bi = 0; bi < 4; bi++)
-        for (int bj = 0; bj < 4; bj++) {
-            const bool low = bi >= bj;
-            const double* ls = Lb + (low ? blk(bi, bj) : 0) * SBSZ;
-            const double* ws = Wb + (low ? blk(bi, bj) : 0) * SBSZ;
-            const bool vup = bj >= bi;
-            const double* vs = Wb + (vup ? blk(bj, bi) : 0) * SBSZ;
-            for (int e = tid; e < SB * SB; e += 256) {
-                const int r = e >> 5, c = e & 31;
-                const long long gr = bi * SB + r, gc = bj * SB + c;
-                A[gr * ld + gc] = low ? ls[r * SLD + c] : 0.0;
-                W[gr * ldw + gc] = low ? ws[r * SLD + c] : 0.0;
-                if (V) V[gr * ldv + gc] = vup ? vs[c * SLD + r] : 0.0;
-            }
-        }
 }
 
 // ===========================================================================
@@ -399,6 +446,8 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
     GPB_REQUIRE(ld >= n && ldw >= n && (!V || ldv >= n), "leading dimension too small");
     GPB_REQUIRE(A && W && info, "null pointer");
+    GPB_REQUIRE(ld % 2 == 0 && ldw % 2 == 0 && (!V || ldv % 2 == 0), "leading dimensions must be even");
+    GPB_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "W must be 16-byte aligned");
     static bool attr_set = false;
     if (!attr_set) {
         GPB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
