@@ -1,4 +1,4 @@
-"""BASELINE.json configs C1, C3, C4, C5 on the GPU(s): timing + parity / size-independent checks.
+"""BASELINE.json configs C1 - C5 on the GPU(s): timing + parity / size-independent checks.
 Single process:  python tests/gpu_configs.py [c1 c3 c4 c5]
 Multi GPU:       torchrun --nproc-per-node G tests/gpu_configs.py c3 c4      (test points / candidates shard)
 Prints one JSON line per config (rank 0) and appends them to gpurun_out/configs.jsonl."""
@@ -71,6 +71,82 @@ def c1():
     dt = (time.perf_counter() - t0) / reps
     emit(dict(config="C1", metric="bundles/s (log_lh+grad+mean+cov, N=50, M=100)", value=1 / dt,
               ms_per_bundle=dt * 1e3, parity_vs_reference=errs))
+
+
+def c2():
+    """Gaussian N=4096, ONE GP through the public API (cold cache): Kxx build + Cholesky + log_lh /
+    dloglh_dtheta / d2lh_dtheta2; parity against the golden vectors of the unmodified reference;
+    plus the factorisation alone and the batched evaluator at several batch sizes."""
+    if RANK != 0:
+        return
+    from gaussian_processes_b200 import engine
+    g = golden("gp_c2_n4096")
+    n = 4096
+    x, y = synth_xy(n, 0)
+    out = dict(config="C2", n=n)
+
+    def fresh():
+        return gpb.GP(gpb.GaussianKernel(1.0, 0.5), x, y, s=1.0)
+    gp = fresh()
+    gp.log_lh, gp.dloglh_dtheta, gp.d2loglh_normalised()          # warm (allocator, module load)
+    out["parity_vs_reference"] = dict(
+        log_lh=rel(gp.log_lh, g["log_lh"]), dloglh=rel(gp.dloglh_dtheta, g["dloglh_dtheta"]),
+        d2lh_norm=rel(gp.d2loglh_normalised(), g["d2lh_norm"]), lh=float(gp.lh),
+        d2lh_is_zero=bool(np.all(gp.d2lh_dtheta2 == 0)), alpha=rel(gp.inv_Kxx_y, g["inv_Kxx_y"]),
+        inv_Kxx_diag=rel(np.diag(gp.inv_Kxx), g["inv_Kxx_diag"]), Lxx_diag=rel(np.diag(gp.Lxx), g["Lxx_diag"]),
+        mean=rel(gp.mean(g["xo"]), g["mean"]), cov=rel(gp.cov(g["xo"]), g["cov"]),
+        dm=rel(gp.dm_dtheta(g["xo"]), g["dm_dtheta"]))
+    reps = 5
+    lat = {}
+    for name, fn in (("log_lh", lambda q: q.log_lh),
+                     ("log_lh+dloglh", lambda q: (q.log_lh, q.dloglh_dtheta)),
+                     ("log_lh+dloglh+d2lh", lambda q: (q.log_lh, q.dloglh_dtheta, q.d2loglh_normalised()))):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(reps):
+            gp.set_param("w", 0.5 + 1e-7 * (k + 1))               # setters clear the memo (gp.py:231-240)
+            fn(gp)
+        torch.cuda.synchronize()
+        lat[name + "_ms"] = (time.perf_counter() - t0) / reps * 1e3
+    out["single_gp_cold_latency"] = lat
+    # factorisation alone, device-timed
+    e = gp._engine()
+    for nm, nn in (("potrf_n4096", 4096), ("potrf_n8192", 8192), ("potrf_n16384", 16384)):
+        xx, yy = synth_xy(nn, 0)
+        eng = engine.Engine(engine.GAUSSIAN, (1.0, 0.5), 1.0, xx, yy)
+        eng.factor()
+        best = 1e9
+        for k in range(3):
+            eng._c.clear()
+            L = eng.build(eng.dx, nn, eng.dx, nn, nn, nn, 1, add_diag=True, pad_identity=True)[0]
+            W, V, info = D.empty(nn, nn), D.empty(nn, nn), D.izeros(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            gpb._lib.call("gpb_potrf", D.ptr(L), nn, nn, 0, 1, D.ptr(W), nn, 0, D.ptr(V), nn, 0, D.ptr(info), D.stream_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[nm] = dict(ms=best, tflops=nn ** 3 / 3 / best / 1e9)
+        del eng, L, W, V
+    # batched evaluator vs batch size
+    bs = {}
+    for B in (1, 2, 4, 8, 16, 32):
+        ev = engine.BatchEvaluator(engine.GAUSSIAN, x, y, max_batch=B)
+        rng = np.random.RandomState(B)
+        th = np.array([1.0, 0.5, 1.0]) * (1 + 0.05 * rng.uniform(-1, 1, (B, 3)))
+        ev.eval_device(th); ev.eval_device(th)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(3):
+            ev.eval_device(th + 1e-6 * k)
+        e1.record()
+        torch.cuda.synchronize()
+        bs[str(B)] = 3 * B / (e0.elapsed_time(e1) * 1e-3)
+        del ev
+    out["batched_evals_per_s_by_batch"] = bs
+    emit(out)
 
 
 def c3():
@@ -216,7 +292,7 @@ def c5():
 
 
 if __name__ == "__main__":
-    which = [a for a in sys.argv[1:] if a in ("c1", "c3", "c4", "c5")] or ["c1", "c3", "c4", "c5"]
+    which = [a for a in sys.argv[1:] if a in ("c1", "c2", "c3", "c4", "c5")] or ["c1", "c2", "c3", "c4", "c5"]
     for w in which:
         try:
             globals()[w]()
