@@ -202,6 +202,69 @@ static int pool_reserve(size_t bytes) {
     return GPB_OK;
 }
 
+// ---- device -> host downloads ---------------------------------------------------------
+// A pageable destination is filled through three pinned staging slots: the DMA of chunk
+// k+1 runs while the host copies chunk k out of its slot, so the PCIe link never waits for
+// the driver's own (slower, serialised) pageable path.
+#define GPB_STAGE_SLOTS 3
+#define GPB_STAGE_BYTES ((size_t)8 << 20)
+static void* g_stage[GPB_STAGE_SLOTS];
+static cudaEvent_t g_stage_ev[GPB_STAGE_SLOTS];
+static int stage_init() {
+    if (g_stage[0]) return GPB_OK;
+    for (int i = 0; i < GPB_STAGE_SLOTS; i++) {
+        GPB_CUDA(cudaHostAlloc(&g_stage[i], GPB_STAGE_BYTES, cudaHostAllocDefault));
+        GPB_CUDA(cudaEventCreateWithFlags(&g_stage_ev[i], cudaEventDisableTiming));
+    }
+    return GPB_OK;
+}
+static int d2h_staged(double* dst, long long ldd, const double* src, long long lds, long long rows,
+                      long long cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return GPB_OK;
+    int stt = stage_init();
+    if (stt) return stt;
+    const long long slot_doubles = (long long)(GPB_STAGE_BYTES / 8);
+    if (ldd == cols && lds == cols && rows > 1 && (cols > slot_doubles || cols < 4096)) {
+        // contiguous on both sides: re-tile as rows of one slot quarter (plus a remainder row)
+        const long long total = rows * cols, w = slot_doubles / 4, full = total / w;
+        if (full > 0) { stt = d2h_staged(dst, w, src, w, full, w, st); if (stt) return stt; }
+        if (total > full * w) return d2h_staged(dst + full * w, total - full * w, src + full * w, total - full * w, 1, total - full * w, st);
+        return GPB_OK;
+    }
+    if (cols > slot_doubles) {           // a single row longer than a slot: split by columns
+        for (long long c0 = 0; c0 < cols; c0 += slot_doubles) {
+            const long long cw = (cols - c0 < slot_doubles) ? cols - c0 : slot_doubles;
+            stt = d2h_staged(dst + c0, ldd, src + c0, lds, rows, cw, st);
+            if (stt) return stt;
+        }
+        return GPB_OK;
+    }
+    const long long rpc = slot_doubles / cols;     // rows per chunk (>= 1)
+    const long long nchunks = (rows + rpc - 1) / rpc;
+    auto drain = [&](long long c) -> int {
+        const int slot = (int)(c % GPB_STAGE_SLOTS);
+        GPB_CUDA(cudaEventSynchronize(g_stage_ev[slot]));
+        const long long r0 = c * rpc, nr = (rows - r0 < rpc) ? rows - r0 : rpc;
+        const double* h = (const double*)g_stage[slot];
+        if (ldd == cols) memcpy(dst + r0 * ldd, h, (size_t)nr * cols * 8);
+        else for (long long r = 0; r < nr; r++) memcpy(dst + (r0 + r) * ldd, h + r * cols, (size_t)cols * 8);
+        return GPB_OK;
+    };
+    for (long long c = 0; c < nchunks; c++) {
+        if (c >= GPB_STAGE_SLOTS) { stt = drain(c - GPB_STAGE_SLOTS); if (stt) return stt; }
+        const int slot = (int)(c % GPB_STAGE_SLOTS);
+        const long long r0 = c * rpc, nr = (rows - r0 < rpc) ? rows - r0 : rpc;
+        GPB_CUDA(cudaMemcpy2DAsync(g_stage[slot], (size_t)cols * 8, src + r0 * lds, (size_t)lds * 8,
+                                   (size_t)cols * 8, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        GPB_CUDA(cudaEventRecord(g_stage_ev[slot], st));
+    }
+    for (long long c = (nchunks > GPB_STAGE_SLOTS ? nchunks - GPB_STAGE_SLOTS : 0); c < nchunks; c++) {
+        stt = drain(c);
+        if (stt) return stt;
+    }
+    return GPB_OK;
+}
+
 extern "C" {
 
 int gpb_version(void) { return 100; }
@@ -287,6 +350,19 @@ int gpb_tril(double* A, int64_t n, int64_t ld, void* stream) {
 int gpb_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
                void* stream) {
     return gpb_launch_copy2d(dst, ldd, src, lds, rows, cols, 0, 0, 1, S(stream));
+}
+
+int gpb_download_2d(double* dst_host, int64_t ld_host, const double* src_dev, int64_t ld_dev,
+                    int64_t rows, int64_t cols, int dst_pinned, void* stream) {
+    GPB_REQUIRE(rows >= 0 && cols >= 0 && ld_host >= cols && ld_dev >= cols, "bad extents");
+    if (rows == 0 || cols == 0) return GPB_OK;
+    GPB_REQUIRE(dst_host && src_dev, "null pointer");
+    if (dst_pinned) {          // page-locked destination: one asynchronous strided DMA
+        GPB_CUDA(cudaMemcpy2DAsync(dst_host, (size_t)ld_host * 8, src_dev, (size_t)ld_dev * 8, (size_t)cols * 8,
+                                   (size_t)rows, cudaMemcpyDeviceToHost, S(stream)));
+        return GPB_OK;
+    }
+    return d2h_staged(dst_host, ld_host, src_dev, ld_dev, rows, cols, S(stream));
 }
 
 int gpb_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
@@ -453,7 +529,9 @@ int gpb_kernel_slices_host(int kind, unsigned slice_mask, double* out, const dou
     GPB_CUDA(cudaMemcpyAsync(dx2, x2, n2 * 8, cudaMemcpyHostToDevice, 0));
     stt = gpb_kernel_build(kind, theta, 0.0, dx1, n1, dx2, n2, n1, n2, slice_mask, dout, n2, n1 * n2, 0, 0, nullptr);
     if (stt) return stt;
-    GPB_CUDA(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, 0));
+    // ns slices of n1 x n2 are contiguous on both sides: one [ns*n1, n2] strided download
+    stt = d2h_staged(out, n2, dout, n2, (long long)ns * n1, n2, 0);
+    if (stt) return stt;
     GPB_CUDA(cudaStreamSynchronize(0));
     return GPB_OK;
 }

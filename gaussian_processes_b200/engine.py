@@ -118,7 +118,7 @@ class Engine(object):
         self.require_pd()
         L = self._c["L"].clone()
         call("gpb_tril", D.ptr(L), self.npad, self.npad, D.stream_ptr())
-        return D.to_host(L[:self.n, :self.n]).copy()
+        return D.download_2d(L, self.n, self.n)
 
     def alpha(self):
         """K^-1 y by forward/backward substitution (cho_solve, gp.py:332-334); [npad], pad = 0."""
@@ -274,8 +274,40 @@ class Engine(object):
                  iarr([0]), iarr([0]), darr([1.0]), parr([D.ptr(a)]), 1, parr([D.ptr(out)]), D.stream_ptr())
         return D.to_host(out[:m]).copy()
 
-    def cov(self, xo):
-        """K(xo,xo) - K(xo,x) K^-1 K(x,xo) as Kxoxo - Z Z^T with Z = K(xo,x) L^-T (gp.py:599-625)."""
+    def _rows_out(self, C, rows, cols, blocks, host=True):
+        """Download row blocks of the device matrix ``C`` as they are produced.  ``blocks`` yields
+        (r0, r1) after enqueuing the work that completes rows [r0, r1) on the compute stream; each
+        block's DMA runs on the copy stream behind an event, overlapping the next block's GEMMs."""
+        if not host:                 # device-resident result (timing / chaining): just run the blocks
+            for _ in blocks:
+                pass
+            return C[:rows, :cols]
+        out, pinned = D.host_array(rows, cols)
+        cs = D.copy_stream() if pinned else None
+        for r0, r1 in blocks:
+            r1 = min(r1, rows)
+            if r1 <= r0:
+                continue
+            if pinned:
+                cs.wait_stream(torch.cuda.current_stream())
+                D.download_2d(C, r1 - r0, cols, out=out, pinned=True, r0=r0, stream=cs, sync=False)
+            else:
+                D.download_2d(C, r1 - r0, cols, out=out, pinned=False, r0=r0)
+        if pinned:
+            cs.synchronize()
+            torch.cuda.current_stream().wait_stream(cs)      # C may be freed / reused after this
+        return out
+
+    @staticmethod
+    def _panel(mp):
+        """Row-panel height for pipelined result downloads: ~8 panels, multiples of 128, >= 1024."""
+        return max(1024, D.roundup(mp // 8))
+
+    def cov(self, xo, host=True):
+        """K(xo,xo) - K(xo,x) K^-1 K(x,xo) as Kxoxo - Z Z^T with Z = K(xo,x) L^-T (gp.py:599-625).
+        Only tiles on or below the diagonal are computed (mirrored store).  Row panels run bottom-up
+        so that each panel is final -- its upper part was mirrored by the panels below it -- when its
+        own GEMM ends, and its download overlaps the next panel's GEMM."""
         W, _ = self.inv_factor()
         m = int(xo.size)
         if m == 0:
@@ -285,27 +317,49 @@ class Engine(object):
         Kxox = self.build(dxo, m, self.dx, self.n, mp, self.npad, 1)[0]
         Z = D.empty(mp, self.npad)
         self.gemm(Kxox, W, Z, mp, self.npad, self.npad, b_tri=1)
+        del Kxox
         C = self.build(dxo, m, dxo, m, mp, mp, 1)[0]
-        self.gemm(Z, Z, C, mp, mp, self.npad, alpha=-1.0, beta=1.0, lower_only=1, Ct=C)
-        return D.to_host(C[:m, :m]).copy()
+        P = self._panel(mp)
 
-    def cov_rows(self, xo, lo, hi):
+        def blocks():
+            for r1 in range(mp, 0, -P):
+                r0 = max(0, r1 - P)
+                if r0 > 0:      # C[r0:r1, :r0] -= Z[r0:r1] Z[:r0]^T, mirrored into C[:r0, r0:r1]
+                    self.gemm(Z[r0:r1], Z[:r0], C[r0:r1, :r0], r1 - r0, r0, self.npad, alpha=-1.0, beta=1.0,
+                              Ct=C[:r0, r0:r1])
+                Cd = C[r0:r1, r0:r1]
+                self.gemm(Z[r0:r1], Z[r0:r1], Cd, r1 - r0, r1 - r0, self.npad, alpha=-1.0, beta=1.0,
+                          lower_only=1, Ct=Cd)
+                yield r0, r1
+        return self._rows_out(C, m, m, blocks(), host)
+
+    def cov_rows(self, xo, lo, hi, host=True):
         """Rows lo:hi of cov(xo) -- the unit of test-point sharding: needs no peer
-        data.  U = K(xo_r, x) Ki, then K(xo_r, xo) - U K(xo, x)^T; 2 N^2 m_r + 2 N M m_r flop."""
-        Ki = self.Ki()
+        data.  U = K(xo_r, x) Ki, then K(xo_r, xo) - U K(xo, x)^T; 2 N^2 m_r + 2 N M m_r flop.
+        The whole range (one shard) takes the symmetric path of ``cov``."""
         m, mb = int(xo.size), int(hi - lo)
         if mb <= 0 or m == 0:
             return np.empty((max(mb, 0), m), dtype=DTYPE)
+        if lo == 0 and hi == m:
+            return self.cov(xo, host)
+        Ki = self.Ki()
         mp, mbp = D.roundup(m), D.roundup(mb)
         dxo = D.to_device(xo)
         dxr = dxo[lo:hi]
         Kr = self.build(dxr, mb, self.dx, self.n, mbp, self.npad, 1)[0]
         U = D.empty(mbp, self.npad)
         self.gemm(Kr, Ki, U, mbp, self.npad, self.npad)           # Ki symmetric: NT form is K(xo_r,x) Ki
+        del Kr
         Kall = self.build(dxo, m, self.dx, self.n, mp, self.npad, 1)[0]
         C = self.build(dxr, mb, dxo, m, mbp, mp, 1)[0]
-        self.gemm(U, Kall, C, mbp, mp, self.npad, alpha=-1.0, beta=1.0)
-        return D.to_host(C[:mb, :m]).copy()
+        P = self._panel(mbp)
+
+        def blocks():
+            for r0 in range(0, mbp, P):
+                r1 = min(mbp, r0 + P)
+                self.gemm(U[r0:r1], Kall, C[r0:r1], r1 - r0, mp, self.npad, alpha=-1.0, beta=1.0)
+                yield r0, r1
+        return self._rows_out(C, mb, m, blocks(), host)
 
     def solve_residual(self):
         """max |Kxx alpha - y| / max |y| computed on the device with regenerated kernel tiles

@@ -192,7 +192,7 @@ class GP(object):
         r"""Kernel covariance matrix :math:`K(x_i, x_j) + s^2\delta_{ij}` (:math:`n\times n`)."""
         e = self._engine()
         from . import device as D
-        return D.to_host(e.Kxx()[:e.n, :e.n]).copy()
+        return D.download_2d(e.Kxx(), e.n, e.n)
 
     @memoprop
     def Kxx_J(self):
@@ -216,7 +216,7 @@ class GP(object):
         e = self._engine()
         e.require_pd()
         from . import device as D
-        return D.to_host(e.Ki()[:e.n, :e.n]).copy()
+        return D.download_2d(e.Ki(), e.n, e.n)
 
     @memoprop
     def inv_Kxx_y(self):

@@ -92,6 +92,13 @@ int gpb_lauum(const double* V, int64_t n, int64_t ldv, int64_t stride_v, int bat
 int gpb_tril(double* A, int64_t n, int64_t ld, void* stream);
 int gpb_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows,
                int64_t cols, void* stream);
+/* rows x cols block, device -> HOST.  dst_pinned != 0: the destination is page-locked, one
+ * asynchronous strided DMA is enqueued on `stream` (the caller synchronises).  Otherwise the
+ * block is pipelined through pinned staging slots (DMA of chunk k+1 overlaps the host copy
+ * of chunk k) and the call returns when dst_host is complete.  This is how matrix-valued
+ * results (GP.cov gp.py:625, Kxx, Lxx, inv_Kxx, kernel slices) reach numpy arrays.          */
+int gpb_download_2d(double* dst_host, int64_t ld_host, const double* src_dev, int64_t ld_dev,
+                    int64_t rows, int64_t cols, int dst_pinned, void* stream);
 
 /* C = beta*C + alpha * A * B^T on FP64 tensor cores (DMMA); M, N multiples of 128, K of 16.
  * a_tri/b_tri: 0 dense, 1 lower (A[i][k] = 0 for k > i), 2 upper (k < i): zero tiles

@@ -188,13 +188,27 @@ def c3():
     mean_r = gp.mean(xo[lo:hi])
     torch.cuda.synchronize()
     tm = maxtime(time.perf_counter() - t0)
+    tcs = []
+    cov_r = None
+    for rep in range(3):             # rep 0 pays the one-time page-locking of the result buffer
+        del cov_r
+        sync()
+        t0 = time.perf_counter()
+        cov_r = gp.cov_rows(xo, lo, hi)
+        torch.cuda.synchronize()
+        tcs.append(maxtime(time.perf_counter() - t0))
+    tc = min(tcs[1:])
     sync()
     t0 = time.perf_counter()
-    cov_r = gp.cov_rows(xo, lo, hi)
+    dev = e.cov_rows(xo, lo, hi, host=False)
     torch.cuda.synchronize()
-    tc = maxtime(time.perf_counter() - t0)
+    tdev = maxtime(time.perf_counter() - t0)
+    del dev
     out.update(mean_test_pts_per_s=m / tm, cov_test_pts_per_s=m / tc, mean_ms=tm * 1e3, cov_rows_ms=tc * 1e3,
-               cov_includes="D2H of the [m_r, M] row block")
+               cov_rows_first_call_ms=tcs[0] * 1e3, cov_rows_device_only_ms=tdev * 1e3,
+               cov_result_GB=cov_r.nbytes / 1e9,
+               cov_includes="Kxox/Kxoxo builds + GEMMs + D2H of the [m_r, M] row block into a numpy array "
+                            "(page-locked result pool, panel downloads overlapped with the GEMMs)")
     # checks: symmetric block, agreement with the Z Z^T path on a sub-block, oracle on a small sub-problem
     if RANK == 0:
         sub = gp.cov(xo[lo:lo + 300])
@@ -258,11 +272,23 @@ def c5():
     t2 = time.perf_counter()
     out.update(info=info, potrf_ms=(t1 - t0) * 1e3, potrf_tflops=n ** 3 / 3 / (t1 - t0) / 1e12,
                solve_loglh_ms=(t2 - t1) * 1e3, log_lh=float(llh), solve_residual=e.solve_residual())
+    t3s = []
+    cov = None
+    for rep in range(2):
+        del cov
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cov = gp.cov(xo)
+        torch.cuda.synchronize()
+        t3s.append(time.perf_counter() - t0)
+    t3 = t3s[1]
     t0 = time.perf_counter()
-    cov = gp.cov(xo)
+    dev = e.cov(xo, host=False)
     torch.cuda.synchronize()
-    t3 = time.perf_counter() - t0
-    out.update(cov_ms=t3 * 1e3, cov_test_pts_per_s=m / t3, cov_includes="trtri + Z=Kxox L^-T + Kxoxo - Z Z^T + D2H of 0.5 GB")
+    tdev = time.perf_counter() - t0
+    del dev
+    out.update(cov_ms=t3 * 1e3, cov_first_call_ms=t3s[0] * 1e3, cov_device_only_ms=tdev * 1e3, cov_test_pts_per_s=m / t3,
+               cov_includes="first call: trtri + Z=Kxox L^-T + Kxoxo - Z Z^T + D2H of 0.5 GB; later calls reuse L^-1")
     t0 = time.perf_counter()
     mean = gp.mean(xo)
     torch.cuda.synchronize()
