@@ -18,6 +18,7 @@
 // has 8 warps and two CTAs share an SM (4 warps per SMSP).  cp.async multi-stage pipeline.
 // All extents are multiples of the tile (buffers are padded by the host layer), so there is
 // no edge predication in the main loop.
+#include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "launch.h"
@@ -182,6 +183,195 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
     }
 }
 
+
+// ===========================================================================
+// TMA + mbarrier variant (default).  Same tile and warp layout as above, but the operand
+// panels are staged by the TMA unit (cp.async.bulk.tensor, one elected producer thread)
+// into 128B-swizzled shared memory, and consumers synchronise per stage through
+// full/empty mbarriers -- there is no CTA-wide barrier in the main loop, so a DMMA warp
+// only ever waits for data, never for its siblings.
+//   stage = A box {16 k, BM rows} + B box {16 k, 128 rows}, rows of 128 bytes, 16-byte chunk
+//   index XOR-ed with (row & 7): fragment loads (8 rows x 4 k per instruction) touch every
+//   bank group exactly twice = the 2-wavefront minimum of a 256-byte warp load.
+// ===========================================================================
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int BM> struct TmaCfg {
+    static constexpr int CONSUMERS = BM * 4;               // threads: (BM/32) x 4 warps of 32 x 32
+    static constexpr int THREADS = CONSUMERS + 32;         // + one producer warp
+    static constexpr int STAGES = (BM == 128) ? 6 : 4;
+    static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 2 * STAGES * 8;
+    static constexpr int MIN_CTAS = (BM == 128) ? 1 : 2;
+};
+
+template <int BM>
+__global__ void __launch_bounds__(TmaCfg<BM>::THREADS, TmaCfg<BM>::MIN_CTAS)
+gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+    using Cfg = TmaCfg<BM>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms are 1024-byte aligned
+    const unsigned char* tiles = smem_raw + (base - smem_u32(smem_raw));  // generic-space view for fragment loads
+    const unsigned bar_full = base + STAGES * Cfg::STAGE_BYTES;           // STAGES x 8 bytes
+    const unsigned bar_empty = bar_full + STAGES * 8;
+
+    // ---- tile coordinates (identical to the cp.async kernel) -------------------------------
+    int ti, tj;
+    bool diag_tile = false;
+    int diag_sub = -1;
+    if (p.lower_only) {
+        constexpr int RPG = 128 / BM;
+        const int t = blockIdx.x / RPG, sub = blockIdx.x % RPG;
+        int i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((long long)(i + 1) * (i + 2) / 2 <= t) i++;
+        while ((long long)i * (i + 1) / 2 > t) i--;
+        tj = t - i * (i + 1) / 2;
+        ti = i * RPG + sub;
+        diag_tile = (tj == i);
+        if (diag_tile && RPG == 2) diag_sub = sub;
+    } else {
+        ti = (p.a_tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+        tj = blockIdx.y;
+    }
+    const int m0 = ti * BM, n0 = tj * BN;
+    const long long bz = blockIdx.z / p.nb1, bt = blockIdx.z % p.nb1;
+
+    int kbeg = 0, kend = p.K;
+    if (p.a_tri == 1) kend = min(kend, m0 + BM + p.a_off);
+    else if (p.a_tri == 2) kbeg = max(kbeg, m0 + p.a_off);
+    if (p.b_tri == 1) kend = min(kend, n0 + BN + p.b_off);
+    else if (p.b_tri == 2) kbeg = max(kbeg, n0 + p.b_off);
+    kbeg = max(kbeg, 0) & ~(BK - 1);
+    kend = min((kend + BK - 1) & ~(BK - 1), p.K);
+    const int nk = (kend > kbeg) ? (kend - kbeg) / BK : 0;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(bar_full + s * 8, 1);                       // producer's expect_tx arrival (+ TMA bytes)
+            mbar_init(bar_empty + s * 8, Cfg::CONSUMERS / 32);    // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wid == Cfg::CONSUMERS / 32) {
+        // ===== producer warp: one elected lane drives the TMA unit =====
+        if (lane == 0) {
+            // batch offsets become (row, column) coordinates of the tensor map (base = p.A / p.B)
+            const long long offA = bz * p.sA + bt * p.tA, offB = bz * p.sB + bt * p.tB;
+            const int arow = (int)(offA / p.lda) + m0, acol = (int)(offA % p.lda) + kbeg;
+            const int brow = (int)(offB / p.ldb) + n0, bcol = (int)(offB % p.ldb) + kbeg;
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % STAGES;
+                const unsigned ph = (unsigned)(kt / STAGES) & 1u;
+                mbar_wait(bar_empty + s * 8, ph ^ 1u);            // first round passes immediately
+                mbar_expect_tx(bar_full + s * 8, Cfg::STAGE_BYTES);
+                const unsigned sa = base + s * Cfg::STAGE_BYTES;
+                tma_load_2d(sa, &mapA, acol + kt * BK, arow, bar_full + s * 8);
+                tma_load_2d(sa + Cfg::A_BYTES, &mapB, bcol + kt * BK, brow, bar_full + s * 8);
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int wm = wid >> 2, wn = wid & 3;
+    const int g = lane >> 2, t = lane & 3;
+    const bool skip_mma = (diag_sub == 0) && (wn >= 2);
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    // swizzled byte offset of element (row = 8*q + g, k = 4*kk + t) inside a tile: row*128 + sw[kk]
+    unsigned sw[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) sw[kk] = (unsigned)((((kk * 2 + (t >> 1)) ^ g) << 4) + ((t & 1) << 3));
+    const unsigned a_row = (unsigned)((wm * 32 + g) * 128), b_row = (unsigned)(Cfg::A_BYTES + (wn * 32 + g) * 128);
+
+    for (int kt = 0; kt < nk; kt++) {
+        const int s = kt % STAGES;
+        mbar_wait(bar_full + s * 8, (unsigned)(kt / STAGES) & 1u);
+        if (!skip_mma) {
+            const unsigned char* sa = tiles + s * Cfg::STAGE_BYTES + a_row;
+            const unsigned char* sb = tiles + s * Cfg::STAGE_BYTES + b_row;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; kk++) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double*>(sa + sw[kk] + mi * 1024);
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double*>(sb + sw[kk] + ni * 1024);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + s * 8);            // this warp is done with the stage
+    }
+
+    // ---- epilogue (registers -> global, optional mirrored store) ------------------------------
+    double* C = p.C + bz * p.sC + bt * p.tC;
+    double* Ct = p.Ct ? p.Ct + bz * p.sCt + bt * p.tCt : nullptr;
+    bool mirror = (Ct != nullptr) && !(p.lower_only && diag_tile && Ct == C);
+    if (Ct != nullptr && diag_sub == 1 && wn < 2) mirror = true;
+    if (skip_mma) return;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const int r = m0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int c = n0 + wn * 32 + ni * 8 + 2 * t;
+            double2* dst = reinterpret_cast<double2*>(C + (long long)r * p.ldc + c);
+            double v0 = alpha * acc[mi][ni][0], v1 = alpha * acc[mi][ni][1];
+            if (beta != 0.0) {
+                const double2 old = *dst;
+                v0 += beta * old.x;
+                v1 += beta * old.y;
+            }
+            *dst = make_double2(v0, v1);
+            if (mirror) {
+                Ct[(long long)c * p.ldct + r] = v0;
+                Ct[(long long)(c + 1) * p.ldct + r] = v1;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 
@@ -208,6 +398,64 @@ static int launch_cfg(const GpbGemm& p, int batch, cudaStream_t st) {
     return GPB_OK;
 }
 
+// ---- TMA descriptors ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int encode_init() {
+    if (g_encode) return GPB_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GPB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    GPB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    g_encode = (EncodeTiledFn)fn;
+    return GPB_OK;
+}
+// rows x ld view starting at `ptr`; box = {16 doubles (one 128-byte swizzle row), box_rows}
+static int make_map(CUtensorMap* m, const double* ptr, long long ld, long long rows, int box_rows) {
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        gpb_set_error("cuTensorMapEncodeTiled failed (%d): ptr %p ld %lld rows %lld", (int)r, (const void*)ptr, ld, rows);
+        return GPB_ERR_CUDA;
+    }
+    return GPB_OK;
+}
+
+template <int BM>
+static int launch_tma(const GpbGemm& p, int batch, cudaStream_t st) {
+    using Cfg = TmaCfg<BM>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CUDA(cudaFuncSetAttribute(gemm_nt_tma_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int stt = encode_init();
+    if (stt) return stt;
+    // the map's row extent covers the furthest batch member: offsets are turned into (row, column)
+    const long long offA = (long long)(batch - 1) * p.sA + (long long)(p.nb1 - 1) * p.tA;
+    const long long offB = (long long)(batch - 1) * p.sB + (long long)(p.nb1 - 1) * p.tB;
+    CUtensorMap mapA, mapB;
+    stt = make_map(&mapA, p.A, p.lda, offA / p.lda + p.M, BM);
+    if (stt) return stt;
+    stt = make_map(&mapB, p.B, p.ldb, offB / p.ldb + p.N, BN);
+    if (stt) return stt;
+    dim3 grid;
+    const int tm = p.M / BM, tn = p.N / BN;
+    if (p.lower_only) grid = dim3((unsigned)((long long)tn * (tn + 1) / 2 * (128 / BM)), 1, (unsigned)(batch * p.nb1));
+    else grid = dim3((unsigned)tm, (unsigned)tn, (unsigned)(batch * p.nb1));
+    GpbProfScope prof(GPB_KC_GEMM, st);
+    gemm_nt_tma_kernel<BM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, mapA, mapB);
+    GPB_LAUNCH_CHECK("gemm_nt_tma_kernel");
+    return GPB_OK;
+}
+
 // `batch` = outer batch count; the grid's z extent is batch * p.nb1
 int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st) {
     GPB_REQUIRE(p.M > 0 && p.N > 0 && p.K >= 0, "empty problem");
@@ -217,7 +465,18 @@ int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st) {
     GPB_REQUIRE(p.sA % 2 == 0 && p.sB % 2 == 0 && p.sC % 2 == 0, "batch strides must be even");
     GPB_REQUIRE(p.tA % 2 == 0 && p.tB % 2 == 0 && p.tC % 2 == 0 && p.nb1 >= 1, "inner batch strides must be even");
     GPB_REQUIRE(batch >= 1 && (long long)batch * p.nb1 <= 65535, "bad batch");
+    if (p.lower_only) GPB_REQUIRE(p.M == p.N, "lower_only needs a square output");
+    else GPB_REQUIRE(p.N / BN <= 65535, "too many column tiles");
     int bm = gpb_get_option("gemm_bm");
     if (bm != 64 && bm != 128) bm = 64;     // default: two co-resident 64x128 CTAs per SM
+    // operand staging: TMA (default) whenever batch offsets map onto (row, column) coordinates of one
+    // tensor map -- always the case for the factorisation's own calls; gemm_impl = 1 forces cp.async
+    const long long offA = (long long)(batch - 1) * p.sA + (long long)(p.nb1 - 1) * p.tA;
+    const long long offB = (long long)(batch - 1) * p.sB + (long long)(p.nb1 - 1) * p.tB;
+    const bool tma_ok = p.K > 0 && p.sA >= 0 && p.tA >= 0 && p.sB >= 0 && p.tB >= 0 &&
+                        (offA % p.lda) + p.K <= p.lda && (offB % p.ldb) + p.K <= p.ldb &&
+                        offA / p.lda + p.M < (1LL << 31) && offB / p.ldb + p.N < (1LL << 31) && p.lda < (1LL << 31) && p.ldb < (1LL << 31);
+    if (tma_ok && gpb_get_option("gemm_impl") != 1)
+        return bm == 128 ? launch_tma<128>(p, batch, st) : launch_tma<64>(p, batch, st);
     return bm == 128 ? launch_cfg<128>(p, batch, st) : launch_cfg<64>(p, batch, st);
 }
