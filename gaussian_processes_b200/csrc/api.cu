@@ -437,7 +437,8 @@ static int eval_group(int kind, const double* thetas, int batch, const double* x
     // Kxx + s^2 I straight into the factorisation buffer, identity in the pad
     double* outs[GPB_MAX_SLICES] = {nullptr};
     outs[0] = w.L;
-    stt = gpb_launch_build(kind, nullptr, w.Pb, batch, x, n, x, n, np_, np_, outs, np_, mstride, 1, 1, st);
+    // the factorisation reads the lower triangle only: skip the tiles above it (half the exp work)
+    stt = gpb_launch_build(kind, nullptr, w.Pb, batch, x, n, x, n, np_, np_, outs, np_, mstride, 1, 1, st, 1);
     if (stt) return stt;
     stt = gpb_launch_potrf(w.L, np_, np_, mstride, batch, w.W, np_, mstride, want_grad ? w.V : nullptr, np_, mstride, w.info, st);
     if (stt) return stt;

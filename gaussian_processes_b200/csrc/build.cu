@@ -20,6 +20,8 @@ struct BuildArgs {
     long long bstride;     // batch stride of every out[] slice
     int add_diag;          // slice 0: += s^2 on the index diagonal (gp.py:265)
     int pad_identity;      // slice 0: 1.0 on the diagonal of the pad region
+    int lower_only;        // square x1 == x2 build for the factorisation: only the 32 x 64 tiles that touch
+                           // the lower triangle (whole 64 x 64 diagonal blocks included) are generated
 };
 
 template <int KIND>
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(256) build_kernel(const BuildArgs a) {
     for (int s = 0; s < NS; s++)
         if (a.out[s]) need |= 1u << gpb_slice_to_unique(KIND, s);
 
+    if (a.lower_only && blockIdx.x > blockIdx.y / 2) return;     // tile strictly above the 64-block diagonal
     const long long j0 = ((long long)blockIdx.x * 32 + threadIdx.x) * 2;
     if (j0 >= a.cols) return;
     const bool two = (j0 + 1 < a.cols);
@@ -97,9 +100,10 @@ __global__ void __launch_bounds__(256) build_kernel(const BuildArgs a) {
 int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, const double* x1,
                      long long n1, const double* x2, long long n2, long long rows, long long cols,
                      double* const* out, long long ld, long long bstride, int add_diag,
-                     int pad_identity, cudaStream_t st) {
+                     int pad_identity, cudaStream_t st, int lower_only) {
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(rows >= n1 && cols >= n2 && ld >= cols, "bad extents");
+    GPB_REQUIRE(!lower_only || (rows == cols && n1 == n2), "lower_only needs a square build");
     if (rows == 0 || cols == 0) return GPB_OK;
     BuildArgs a;
     if (P) a.P = *P; else memset(&a.P, 0, sizeof(KParams));
@@ -116,7 +120,7 @@ int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, c
         }
     }
     if (!any) return GPB_OK;
-    a.ld = ld; a.bstride = bstride; a.add_diag = add_diag; a.pad_identity = pad_identity;
+    a.ld = ld; a.bstride = bstride; a.add_diag = add_diag; a.pad_identity = pad_identity; a.lower_only = lower_only;
     dim3 block(32, 8);
     dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 31) / 32), (unsigned)batch);
     GPB_REQUIRE(grid.y <= 65535 && batch <= 65535, "extent too large for the launch grid");
@@ -302,6 +306,79 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const GradArgs a) {
     }
 }
 
+// Gradient fast path (the per-candidate reduction of the batched evaluator): the requested
+// slices are exactly the Jacobian slices in order, so the slice set is a compile-time constant
+// (no run-time picks), two adjacent columns per lane with 128-bit loads, and a register budget
+// that lets three CTAs share an SM.
+template <int KIND>
+__global__ void __launch_bounds__(256, 3) grad_jac_kernel(const GradArgs a) {
+    constexpr int NP = (KIND == GPB_GAUSSIAN) ? 2 : 3;
+    constexpr unsigned NEED = (KIND == GPB_GAUSSIAN) ? 0x6u : 0xEu;
+    __shared__ KParams sP;
+    __shared__ double red[32];
+    load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double* Ki = a.Ki + (long long)blockIdx.z * a.kstride;
+    const double* al = a.alpha + (long long)blockIdx.z * a.astride;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(al) |
+                          reinterpret_cast<uintptr_t>(Ki)) & 15) == 0 && (a.ldk & 1) == 0;
+
+    double t0[NP], t1[NP], tr = 0, aa = 0;
+#pragma unroll
+    for (int q = 0; q < NP; q++) t0[q] = t1[q] = 0.0;
+    for (long long r = (long long)blockIdx.x * 8 + wid; r < a.n; r += (long long)gridDim.x * 8) {
+        const double xi = a.x[r], ar = al[r];
+        const double* row = Ki + r * a.ldk;
+        double q0[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++) q0[q] = 0.0;
+        for (long long c = 2 * lane; c <= r; c += 64) {
+            double xc0, xc1 = 0.0, k0, k1 = 0.0, a0, a1 = 0.0;
+            const bool two = (c + 1 <= r);
+            if (two && vec_ok) {
+                const double2 xv = *reinterpret_cast<const double2*>(a.x + c);
+                const double2 kv = *reinterpret_cast<const double2*>(row + c);
+                const double2 av = *reinterpret_cast<const double2*>(al + c);
+                xc0 = xv.x; xc1 = xv.y; k0 = kv.x; k1 = kv.y; a0 = av.x; a1 = av.y;
+            } else {
+                xc0 = a.x[c]; k0 = row[c]; a0 = al[c];
+                if (two) { xc1 = a.x[c + 1]; k1 = row[c + 1]; a1 = al[c + 1]; }
+            }
+            double u0[10], u1[10];
+            gpb_eval_unique<KIND>(sP, xi - xc0, NEED, u0);
+            // strict lower part counts twice (symmetry), the diagonal once
+            const double w0 = (c < r) ? 2.0 : 1.0;
+            if (c == r) tr += k0;
+            k0 *= w0; a0 *= w0;
+#pragma unroll
+            for (int q = 0; q < NP; q++) { q0[q] += u0[1 + q] * a0; t1[q] += u0[1 + q] * k0; }
+            if (two) {
+                gpb_eval_unique<KIND>(sP, xi - xc1, NEED, u1);
+                const double w1 = (c + 1 < r) ? 2.0 : 1.0;
+                if (c + 1 == r) tr += k1;
+                k1 *= w1; a1 *= w1;
+#pragma unroll
+                for (int q = 0; q < NP; q++) { q0[q] += u1[1 + q] * a1; t1[q] += u1[1 + q] * k1; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; q++) t0[q] += ar * q0[q];
+        if (lane == 0) aa += ar * ar;
+    }
+    double* out = a.partial + ((long long)blockIdx.z * gridDim.x + blockIdx.x) * GPB_RED_WIDTH;
+#pragma unroll
+    for (int q = 0; q < GPB_RED_MAXS; q++) {
+        const double s0 = block_sum(q < NP ? t0[q < NP ? q : 0] : 0.0, red);
+        const double s1 = block_sum(q < NP ? t1[q < NP ? q : 0] : 0.0, red);
+        if (threadIdx.x == 0) { out[q] = s0; out[GPB_RED_MAXS + q] = s1; }
+    }
+    {
+        const double s0 = block_sum(tr, red);
+        const double s1 = block_sum(aa, red);
+        if (threadIdx.x == 0) { out[12] = s0; out[13] = s1; out[14] = 0.0; out[15] = 0.0; }
+    }
+}
+
 // deterministic second stage: out[b][q] = sum_k partial[b][k][q]
 __global__ void __launch_bounds__(256) sum_partials_kernel(const double* partial, int nblk, int width, double* out) {
     __shared__ double red[32];
@@ -342,8 +419,15 @@ int gpb_launch_grad_reduce(int kind, const KParams* P, const KParams* Pb, int ba
     const int nb = gpb_grad_reduce_blocks(n);
     dim3 grid((unsigned)nb, 1, (unsigned)batch);
     GpbProfScope prof(GPB_KC_REDUCE, st);
-    if (kind == GPB_GAUSSIAN) grad_reduce_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
-    else grad_reduce_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
+    bool jac = (nsl == gpb_n_kparams(kind));
+    for (int q = 0; q < nsl; q++) jac = jac && (a.uq[q] == q + 1);
+    if (jac) {
+        if (kind == GPB_GAUSSIAN) grad_jac_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
+        else grad_jac_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (kind == GPB_GAUSSIAN) grad_reduce_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
+        else grad_reduce_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
+    }
     GPB_LAUNCH_CHECK("grad_reduce_kernel");
     sum_partials_kernel<<<batch, 256, 0, st>>>(partial, nb, GPB_RED_WIDTH, out16);
     GPB_LAUNCH_CHECK("sum_partials_kernel");

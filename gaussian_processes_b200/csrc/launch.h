@@ -41,7 +41,7 @@ int gpb_get_option(const char* name);
 int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, const double* x1,
                      long long n1, const double* x2, long long n2, long long rows, long long cols,
                      double* const* out, long long ld, long long bstride, int add_diag,
-                     int pad_identity, cudaStream_t st);
+                     int pad_identity, cudaStream_t st, int lower_only = 0);
 
 int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int batch,
                             const double* x1, long long n1, const double* x2, long long n2,

@@ -45,6 +45,15 @@ constexpr int DIAG_SMEM = ((NBLK + 4 + 1) * SBSZ + SB) * 8;     // L blocks, dia
 
 __device__ __forceinline__ int blk(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
 
+// optional phase timing of the diagonal-block kernel (build with -DGPB_DIAG_CLK; read back with
+// gpb_debug_diag_clk): clock64 stamps of CTA 0 / thread 0 at the phase boundaries.
+#ifdef GPB_DIAG_CLK
+__device__ long long g_diag_clk[64];
+#define DIAG_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define DIAG_STAMP(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(256, 2)
 potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ldw, long long sW,
                   double* V, long long ldv, long long sV, int* info, int col0) {
@@ -59,6 +68,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     if (V) V += (long long)blockIdx.x * sV;
     info += blockIdx.x;
 
+    DIAG_STAMP(0);
     // ---- load the lower block-triangle (all copies in flight before the single wait) -------
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((ld & 1) == 0);
     for (int bi = 0; bi < 4; bi++)
@@ -80,6 +90,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     cp_async_wait<0>();
     __syncthreads();
 
+    DIAG_STAMP(1);
     for (int bb = 0; bb < 4; bb++) {
         // ---- P1 (warp 0): 32x32 Cholesky in registers ------------------------------------
         if (wid == 0) {
@@ -116,6 +127,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             for (int r = 0; r < SB; r++) Ld[r * SLD + lane] = D[r * DLD + lane];
         }
         __syncthreads();
+        DIAG_STAMP(2 + bb * 3);
 
         const int nbelow = 3 - bb;
         if (wid == 0) {
@@ -164,6 +176,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             for (int r = 0; r < SB; r++) Ab[r * SLD + lane] = St[r * DLD + lane];
         }
         __syncthreads();
+        DIAG_STAMP(3 + bb * 3);
 
         // ---- P4: trailing update A_ij -= L_ib L_jb^T, bb < j <= i, on DMMA -------------------
         const int npairs = nbelow * (nbelow + 1) / 2;
@@ -183,6 +196,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             Cb[1] = c1;
         }
         __syncthreads();
+        DIAG_STAMP(4 + bb * 3);
     }
 
     // ---- L is final: stream it out (zeros above the diagonal), which also frees the four
@@ -218,6 +232,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             }
         }
     __syncthreads();
+    DIAG_STAMP(14);
 
     // ---- P5: off-diagonal sub-blocks of W = L^-1 by block distance d:
     //      W_ij = -W_ii * S,  S = sum_{k=j}^{i-1} L_ik W_kj
@@ -269,6 +284,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             }
         }
         __syncthreads();
+        DIAG_STAMP(14 + d);
     }
 }
 
@@ -277,115 +293,185 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
 // CTA i accumulates  sum_j L_ij z_j  as soon as z_j is published (release/acquire
 // flags), then applies the inverted diagonal block.  Tickets make the start order
 // match the dependency order, so spinning CTAs can never starve their producers.
+//
+// The serial chain (block i needs z_{i-1}) is what bounds a single solve, so nothing on
+// it may wait for HBM: the L blocks stream through a cp.async ring of 128 x 32 (forward)
+// or 32 x 128 (backward) chunks that runs AHEAD of the flag waits -- L does not depend
+// on the flags, only the multiply does -- and the inverted diagonal block W_ii sits in
+// registers (64 doubles per thread) from the start of the CTA.  When z_{i-1} lands, block
+// L(i,i-1) is already in shared memory: the step costs one flag round trip, two 128 x 128
+// mat-vecs from on-chip data and one publish.
 // ===========================================================================
 constexpr int TS = GPB_NB;
+constexpr int TR_RING = 4;                    // chunks resident per CTA
+constexpr int TR_FLD = 34;                    // forward chunk row stride (doubles): 16-byte rows, conflict-free 128-bit reads
+constexpr int TR_FCH = TS * TR_FLD;           // forward chunk: 128 rows x 32 columns (padded)
+constexpr int TR_BCH = 32 * TS;               // backward chunk: 32 rows x 128 columns
+constexpr int TRSV_FWD_SMEM = (TR_RING * TR_FCH + 4 * TS) * 8;
+constexpr int TRSV_BWD_SMEM = (TR_RING * TR_BCH + 4 * TS) * 8;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 trsv_fwd_kernel(const double* L, long long ld, long long sL, const double* W, long long ldw, long long sW,
                 const double* y, long long sy, double* z, long long svec, int T, int* flags, int* counter) {
+    extern __shared__ __align__(16) double tsm[];
+    double* ring = tsm;                        // TR_RING chunks
+    double* zs = tsm + TR_RING * TR_FCH;       // current z_j (128)
+    double* red = zs + TS;                     // [2][128] partial sums of the two column halves
+    double* rhs = red + 2 * TS;                // 128
     __shared__ int s_ticket;
-    __shared__ double rhs[TS];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid == 0) s_ticket = atomicAdd(counter, 1);
     __syncthreads();
     const int b = s_ticket / T, i = s_ticket % T;
     L += b * sL; W += b * sW; y += b * sy; z += b * svec; flags += (long long)b * T;
+    const int row = tid & (TS - 1), half = tid >> 7;
 
-    double acc[16];
+    // chunk n = (block j = n / 4, columns j*128 + (n % 4)*32 ..): 8 x 16-byte pieces per thread
+    const int nchunks = 4 * i;
+    const double* Lrow0 = L + (long long)i * TS * ld;
+    auto issue = [&](int n) {
+        if (n < nchunks) {
+            const double* src = Lrow0 + (long long)(n >> 2) * TS + (n & 3) * 32;
+            double* dst = ring + (n % TR_RING) * TR_FCH;
 #pragma unroll
-    for (int rr = 0; rr < 16; rr++) acc[rr] = 0.0;
-    for (int j = 0; j < i; j++) {
-        if (tid == 0) while (ld_acquire(flags + j) == 0) {}
-        __syncthreads();
-        const double* zp = z + (long long)j * TS + lane * 4;
-        const double z0 = __ldcg(zp), z1 = __ldcg(zp + 1), z2 = __ldcg(zp + 2), z3 = __ldcg(zp + 3);
-        const double* Lp = L + ((long long)i * TS + wid * 16) * ld + (long long)j * TS + lane * 4;
+            for (int q = 0; q < 8; q++) {
+                const int p = tid + q * 256, r = p >> 4, pc = p & 15;
+                cp_async16(dst + r * TR_FLD + pc * 2, src + (long long)r * ld + pc * 2);
+            }
+        }
+        cp_async_commit();
+    };
 #pragma unroll
-        for (int rr = 0; rr < 16; rr++) {
-            const double2 a = *reinterpret_cast<const double2*>(Lp + rr * ld);
-            const double2 c = *reinterpret_cast<const double2*>(Lp + rr * ld + 2);
-            acc[rr] += a.x * z0 + a.y * z1 + c.x * z2 + c.y * z3;
+    for (int n = 0; n < TR_RING - 1; n++) issue(n);
+
+    // W_ii[row][half*64 .. +64) -> registers (independent of every flag)
+    double wreg[64];
+    {
+        const double* Wp = W + ((long long)i * TS + row) * ldw + (long long)i * TS + half * 64;
+#pragma unroll
+        for (int k = 0; k < 64; k += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(Wp + k);
+            wreg[k] = v.x; wreg[k + 1] = v.y;
         }
     }
+
+    double acc = 0.0;
+    for (int n = 0; n < nchunks; n++) {
+        cp_async_wait<TR_RING - 2>();
+        if ((n & 3) == 0) {                    // new block j: its z must be published
+            const int j = n >> 2;
+            if (tid == 0) while (ld_acquire(flags + j) == 0) {}
+            __syncthreads();
+            if (tid < TS) zs[tid] = __ldcg(z + (long long)j * TS + tid);
+        }
+        __syncthreads();                       // chunk n landed for all threads; zs visible; slot (n-1) free
+        issue(n + TR_RING - 1);
+        const double* ch = ring + (n % TR_RING) * TR_FCH + row * TR_FLD + half * 16;
+        const double* zp = zs + (n & 3) * 32 + half * 16;
 #pragma unroll
-    for (int rr = 0; rr < 16; rr++) {
-        const double s = warp_sum(acc[rr]);
-        if (lane == 0) rhs[wid * 16 + rr] = y[(long long)i * TS + wid * 16 + rr] - s;
+        for (int k = 0; k < 16; k += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(ch + k);
+            acc = fma(v.x, zp[k], acc);
+            acc = fma(v.y, zp[k + 1], acc);
+        }
+    }
+    cp_async_wait<0>();
+    red[half * TS + row] = acc;
+    __syncthreads();
+    if (tid < TS) rhs[tid] = y[(long long)i * TS + tid] - (red[tid] + red[TS + tid]);
+    __syncthreads();
+    {   // z_i = W_ii * rhs, W_ii from registers
+        double s0 = 0.0, s1 = 0.0;
+        const double* rp = rhs + half * 64;
+#pragma unroll
+        for (int k = 0; k < 64; k += 2) {
+            s0 = fma(wreg[k], rp[k], s0);
+            s1 = fma(wreg[k + 1], rp[k + 1], s1);
+        }
+        red[half * TS + row] = s0 + s1;
     }
     __syncthreads();
-    {   // z_i = W_ii * rhs
-        const double r0 = rhs[lane * 4], r1 = rhs[lane * 4 + 1], r2 = rhs[lane * 4 + 2], r3 = rhs[lane * 4 + 3];
-        const double* Wp = W + ((long long)i * TS + wid * 16) * ldw + (long long)i * TS + lane * 4;
-#pragma unroll
-        for (int rr = 0; rr < 16; rr++) {
-            const double2 a = *reinterpret_cast<const double2*>(Wp + rr * ldw);
-            const double2 c = *reinterpret_cast<const double2*>(Wp + rr * ldw + 2);
-            const double s = warp_sum(a.x * r0 + a.y * r1 + c.x * r2 + c.y * r3);
-            if (lane == 0) z[(long long)i * TS + wid * 16 + rr] = s;
-        }
-    }
+    if (tid < TS) z[(long long)i * TS + tid] = red[tid] + red[TS + tid];
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release(flags + i, 1);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 trsv_bwd_kernel(const double* L, long long ld, long long sL, const double* W, long long ldw, long long sW,
                 const double* z, double* alpha, long long svec, int T, int* flags, int* counter) {
+    extern __shared__ __align__(16) double tsm[];
+    double* ring = tsm;
+    double* as = tsm + TR_RING * TR_BCH;       // current alpha_j (128)
+    double* red = as + TS;                     // [2][128] partial sums of the two row halves
+    double* rhs = red + 2 * TS;
     __shared__ int s_ticket;
-    __shared__ double rhs[TS];
-    __shared__ double red[8][TS];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid == 0) s_ticket = atomicAdd(counter, 1);
     __syncthreads();
     const int b = s_ticket / T, i = T - 1 - (s_ticket % T);
     L += b * sL; W += b * sW; z += b * svec; alpha += b * svec; flags += (long long)b * T;
+    const int col = tid & (TS - 1), rhalf = tid >> 7;
 
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int j = T - 1; j > i; j--) {
-        if (tid == 0) while (ld_acquire(flags + j) == 0) {}
-        __syncthreads();
-        const double* ap = alpha + (long long)j * TS + wid * 16;
-        const double* Lp = L + ((long long)j * TS + wid * 16) * ld + (long long)i * TS + lane * 4;
+    // chunk n = (block j = T-1 - n/4, rows j*128 + (n % 4)*32 .. of column block i)
+    const int nchunks = 4 * (T - 1 - i);
+    auto issue = [&](int n) {
+        if (n < nchunks) {
+            const int j = T - 1 - (n >> 2);
+            const double* src = L + ((long long)j * TS + (n & 3) * 32) * ld + (long long)i * TS;
+            double* dst = ring + (n % TR_RING) * TR_BCH;
 #pragma unroll
-        for (int rr = 0; rr < 16; rr++) {
-            const double ar = __ldcg(ap + rr);
-            const double2 a = *reinterpret_cast<const double2*>(Lp + rr * ld);
-            const double2 c = *reinterpret_cast<const double2*>(Lp + rr * ld + 2);
-            acc[0] += a.x * ar; acc[1] += a.y * ar; acc[2] += c.x * ar; acc[3] += c.y * ar;
+            for (int q = 0; q < 8; q++) {
+                const int p = tid + q * 256, r = p >> 6, pc = p & 63;
+                cp_async16(dst + r * TS + pc * 2, src + (long long)r * ld + pc * 2);
+            }
         }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int n = 0; n < TR_RING - 1; n++) issue(n);
+
+    // W_ii[rhalf*64 .. +64)[col] -> registers: alpha_i = W_ii^T rhs
+    double wreg[64];
+    {
+        const double* Wp = W + ((long long)i * TS + rhalf * 64) * ldw + (long long)i * TS + col;
+#pragma unroll
+        for (int k = 0; k < 64; k++) wreg[k] = Wp[(long long)k * ldw];
     }
-#pragma unroll
-    for (int q = 0; q < 4; q++) red[wid][lane * 4 + q] = acc[q];
-    __syncthreads();
-    if (tid < TS) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) s += red[w][tid];
-        rhs[tid] = z[(long long)i * TS + tid] - s;
-    }
-    __syncthreads();
-    {   // alpha_i = W_ii^T * rhs
-        double a4[4] = {0.0, 0.0, 0.0, 0.0};
-        const double* Wp = W + ((long long)i * TS + wid * 16) * ldw + (long long)i * TS + lane * 4;
-#pragma unroll
-        for (int rr = 0; rr < 16; rr++) {
-            const double rv = rhs[wid * 16 + rr];
-            const double2 a = *reinterpret_cast<const double2*>(Wp + rr * ldw);
-            const double2 c = *reinterpret_cast<const double2*>(Wp + rr * ldw + 2);
-            a4[0] += a.x * rv; a4[1] += a.y * rv; a4[2] += c.x * rv; a4[3] += c.y * rv;
+
+    double acc = 0.0;
+    for (int n = 0; n < nchunks; n++) {
+        cp_async_wait<TR_RING - 2>();
+        if ((n & 3) == 0) {
+            const int j = T - 1 - (n >> 2);
+            if (tid == 0) while (ld_acquire(flags + j) == 0) {}
+            __syncthreads();
+            if (tid < TS) as[tid] = __ldcg(alpha + (long long)j * TS + tid);
         }
         __syncthreads();
+        issue(n + TR_RING - 1);
+        const double* ch = ring + (n % TR_RING) * TR_BCH + (rhalf * 16) * TS + col;
+        const double* ap = as + (n & 3) * 32 + rhalf * 16;
 #pragma unroll
-        for (int q = 0; q < 4; q++) red[wid][lane * 4 + q] = a4[q];
+        for (int k = 0; k < 16; k++) acc = fma(ch[k * TS], ap[k], acc);
+    }
+    cp_async_wait<0>();
+    red[rhalf * TS + col] = acc;
+    __syncthreads();
+    if (tid < TS) rhs[tid] = z[(long long)i * TS + tid] - (red[tid] + red[TS + tid]);
+    __syncthreads();
+    {
+        double s0 = 0.0, s1 = 0.0;
+        const double* rp = rhs + rhalf * 64;
+#pragma unroll
+        for (int k = 0; k < 64; k += 2) {
+            s0 = fma(wreg[k], rp[k], s0);
+            s1 = fma(wreg[k + 1], rp[k + 1], s1);
+        }
+        red[rhalf * TS + col] = s0 + s1;
     }
     __syncthreads();
-    if (tid < TS) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) s += red[w][tid];
-        alpha[(long long)i * TS + tid] = s;
-    }
+    if (tid < TS) alpha[(long long)i * TS + tid] = red[tid] + red[TS + tid];
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release(flags + i, 1);
@@ -440,6 +526,13 @@ __global__ void copy2d_kernel(double* dst, long long ldd, const double* src, lon
 // ---------------------------------------------------------------------------
 // drivers
 // ---------------------------------------------------------------------------
+#ifdef GPB_DIAG_CLK
+extern "C" int gpb_debug_diag_clk(long long* out) {
+    GPB_CUDA(cudaMemcpyFromSymbol(out, g_diag_clk, sizeof(long long) * 64));
+    return GPB_OK;
+}
+#endif
+
 int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
                      cudaStream_t st) {
@@ -583,13 +676,20 @@ int gpb_launch_potrs(const double* L, const double* W, long long n, long long ld
     GPB_REQUIRE(ld % 2 == 0 && ldw % 2 == 0 && sL % 2 == 0 && sW % 2 == 0, "strides must be even");
     const int T = (int)(n / GPB_NB);
     const size_t nfl = (size_t)2 * batch * T + 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CUDA(cudaFuncSetAttribute(trsv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_FWD_SMEM));
+        GPB_CUDA(cudaFuncSetAttribute(trsv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_BWD_SMEM));
+        attr_set = true;
+    }
+    GPB_REQUIRE(((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, "L and W must be 16-byte aligned");
     GPB_CUDA(cudaMemsetAsync(flags, 0, nfl * sizeof(int), st));
     GpbProfScope prof(GPB_KC_SOLVE, st);
     int* fF = flags + 2;
     int* fB = fF + (size_t)batch * T;
-    trsv_fwd_kernel<<<batch * T, 256, 0, st>>>(L, ld, sL, W, ldw, sW, y, sy, z, svec, T, fF, flags);
+    trsv_fwd_kernel<<<batch * T, 256, TRSV_FWD_SMEM, st>>>(L, ld, sL, W, ldw, sW, y, sy, z, svec, T, fF, flags);
     GPB_LAUNCH_CHECK("trsv_fwd_kernel");
-    trsv_bwd_kernel<<<batch * T, 256, 0, st>>>(L, ld, sL, W, ldw, sW, z, alpha, svec, T, fB, flags + 1);
+    trsv_bwd_kernel<<<batch * T, 256, TRSV_BWD_SMEM, st>>>(L, ld, sL, W, ldw, sW, z, alpha, svec, T, fB, flags + 1);
     GPB_LAUNCH_CHECK("trsv_bwd_kernel");
     return GPB_OK;
 }
