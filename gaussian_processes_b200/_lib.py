@@ -64,6 +64,7 @@ _PROTOS = {
     "gpb_gp_eval_host": (c_int, [c_int, dp, c_int, dp, dp, _i64, c_int, dp]),
     "gpb_kernel_slices_host": (c_int, [c_int, c_uint, vp, vp, _i64, vp, _i64, dp]),
     "gpb_microbench_fp64": (c_int, [c_int, c_int, dp, dp]),
+    "gpb_microbench_latency": (c_int, [dp]),
     "gpb_set_option": (c_int, [c_char_p, c_int]),
     "gpb_profile_enable": (None, [c_int]),
     "gpb_profile_read": (c_int, [c_int, dp, POINTER(c_int64)]),

@@ -58,3 +58,87 @@ extern "C" int gpb_microbench_fp64(int use_dmma, int iters, double* tflops, doub
     cudaFree(in);
     return GPB_OK;
 }
+
+// ---- dependent-issue latencies (cycles) of the instructions on the factorisation's serial paths ----
+namespace {
+__global__ void latency_kernel(double* out, double seed) {
+    const int lane = threadIdx.x;
+    double x = seed + lane * 1e-9, y = 1.0 + seed;
+    long long t0, t1;
+    constexpr int R = 256;
+    // DFMA chain
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < R; i++) x = fma(x, y, 1e-9);
+    t1 = clock64();
+    out[0] = (double)(t1 - t0) / R;
+    // rsqrt chain
+    double r = 2.0 + x * 1e-30;
+    t0 = clock64();
+#pragma unroll 8
+    for (int i = 0; i < R; i++) r = rsqrt(r) + 1.5;
+    t1 = clock64();
+    out[1] = (double)(t1 - t0) / R;     // includes one DADD
+    // 64-bit shuffle chain
+    double s = r;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < R; i++) s = __shfl_sync(0xffffffffu, s, (lane + 1) & 31);
+    t1 = clock64();
+    out[2] = (double)(t1 - t0) / R;
+    // dependent DMMA chain
+    double c0 = s, c1 = x;
+    t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < R; i++) dmma884(c0, c1, 1e-3, 1e-3);
+    t1 = clock64();
+    out[3] = (double)(t1 - t0) / R;
+    // 8 independent DMMA accumulators from one warp: issue interval
+    double a[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q][0] = a[q][1] = c0 + q;
+    t0 = clock64();
+#pragma unroll 4
+    for (int i = 0; i < R / 8; i++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) dmma884(a[q][0], a[q][1], 1e-3, 1e-3);
+    t1 = clock64();
+    out[4] = (double)(t1 - t0) / R;
+    // sqrt + divide chain (what rsqrt replaced)
+    double q2 = 2.0 + c1 * 1e-30;
+    t0 = clock64();
+#pragma unroll 8
+    for (int i = 0; i < R; i++) q2 = 1.0 / sqrt(q2) + 1.5;
+    t1 = clock64();
+    out[5] = (double)(t1 - t0) / R;
+    // shared-memory store -> load round trip
+    __shared__ double buf[64];
+    double z = q2;
+    t0 = clock64();
+#pragma unroll 8
+    for (int i = 0; i < R; i++) {
+        buf[lane] = z;
+        __syncwarp();
+        z = buf[(lane + 1) & 31] + 1.0;
+        __syncwarp();
+    }
+    t1 = clock64();
+    out[6] = (double)(t1 - t0) / R;
+    double sum = x + r + s + c0 + c1 + q2 + z;
+#pragma unroll
+    for (int q = 0; q < 8; q++) sum += a[q][0] + a[q][1];
+    out[8 + lane] = sum;
+}
+}  // namespace
+
+extern "C" int gpb_microbench_latency(double* out7) {
+    double* d = nullptr;
+    GPB_CUDA(cudaMalloc(&d, 64 * 8));
+    for (int rep = 0; rep < 2; rep++) {
+        latency_kernel<<<1, 32>>>(d, 0.5);
+        GPB_LAUNCH_CHECK("latency_kernel");
+    }
+    GPB_CUDA(cudaMemcpy(out7, d, 7 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return GPB_OK;
+}

@@ -41,7 +41,7 @@ constexpr int SLD = 36;           // padded stride: 36 = 4 (mod 16) -> conflict-
 constexpr int SBSZ = SB * SLD;
 constexpr int NBLK = 10;
 constexpr int DLD = 33;           // odd stride for lane-per-row accesses
-constexpr int DIAG_SMEM = ((NBLK + 4 + 1) * SBSZ + SB) * 8;     // L blocks, diagonal inverses, staging, 1/diag
+constexpr int DIAG_SMEM = ((NBLK + 4 + 1) * SBSZ + SB + 2 * SB) * 8;   // L blocks, diagonal inverses, spare, 1/diag, column broadcast
 
 __device__ __forceinline__ int blk(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
 
@@ -54,14 +54,72 @@ __device__ long long g_diag_clk[64];
 #define DIAG_STAMP(i) do { } while (0)
 #endif
 
+// 16 x 32 strip (rows hf*16 .. +16) of  acc += sgn * Ablk * Bblk  for 32 x 32 blocks held row-major
+// with stride SLD: eight independent DMMA accumulators per warp, so the ~100-cycle latency of a
+// dependent DMMA chain is covered by issue from the other seven tiles.
+__device__ __forceinline__ void strip_mm(double (&acc)[2][4][2], const double* Ablk, const double* Bblk,
+                                         int hf, int g, int t, double sgn) {
+    const double* Ap = Ablk + (hf * 16 + g) * SLD + t;
+    const double* Bp = Bblk + t * SLD + g;
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+        double a[2], b[4];
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++) a[rt] = sgn * Ap[rt * 8 * SLD + kk * 4];
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) b[ct] = Bp[kk * 4 * SLD + ct * 8];
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
+    }
+}
+
+__device__ __forceinline__ void strip_zero(double (&acc)[2][4][2]) {
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) acc[rt][ct][0] = acc[rt][ct][1] = 0.0;
+}
+
+// strip -> shared block (row-major, stride SLD)
+__device__ __forceinline__ void strip_to_smem(const double (&acc)[2][4][2], double* blkp, int hf, int g, int t) {
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+            double* p = blkp + (hf * 16 + rt * 8 + g) * SLD + ct * 8 + 2 * t;
+            p[0] = acc[rt][ct][0];
+            p[1] = acc[rt][ct][1];
+        }
+}
+
+// strip of W_ij -> global W (row-major) and its transpose into V
+__device__ __forceinline__ void strip_to_wv(const double (&acc)[2][4][2], double* W, long long ldw, double* V,
+                                            long long ldv, int i, int j, int hf, int g, int t) {
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+            const long long gr = i * SB + hf * 16 + rt * 8 + g, gc = j * SB + ct * 8 + 2 * t;
+            *reinterpret_cast<double2*>(W + gr * ldw + gc) = make_double2(acc[rt][ct][0], acc[rt][ct][1]);
+            if (V) {
+                V[gc * ldv + gr] = acc[rt][ct][0];
+                V[(gc + 1) * ldv + gr] = acc[rt][ct][1];
+            }
+        }
+}
+
 __global__ void __launch_bounds__(256, 2)
 potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ldw, long long sW,
                   double* V, long long ldv, long long sV, int* info, int col0) {
     extern __shared__ __align__(16) double sm[];
-    double* Lb = sm;                          // 10 lower sub-blocks of the tile
-    double* Wd = sm + NBLK * SBSZ;            // inverses of the 4 diagonal sub-blocks
-    double* D = Wd + 4 * SBSZ;                // staging block (stride 33 in P1-P3, stride 36 later)
+    double* Lb = sm;                          // 10 lower sub-blocks of the tile: off-diagonal ones with stride
+                                              // SLD (DMMA fragments), diagonal ones with stride DLD (lane = row)
+    double* Wd = sm + NBLK * SBSZ;            // inverses of the 4 diagonal sub-blocks (stride SLD)
+    double* D = Wd + 4 * SBSZ;                // spare block
     double* invd = D + SBSZ;
+    double* colbuf = invd + SB;               // 2 x 32: column k of the 32x32 factor, broadcast to all lanes
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
     A += (long long)blockIdx.x * sA;
     W += (long long)blockIdx.x * sW;
@@ -74,7 +132,12 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     for (int bi = 0; bi < 4; bi++)
         for (int bj = 0; bj <= bi; bj++) {
             double* dst = Lb + blk(bi, bj) * SBSZ;
-            if (vec_ok) {
+            if (bi == bj) {
+                for (int e = tid; e < SB * SB; e += 256) {
+                    const int r = e >> 5, c = e & 31;
+                    cp_async8(dst + r * DLD + c, A + (long long)(bi * SB + r) * ld + bj * SB + c);
+                }
+            } else if (vec_ok) {
                 for (int e = tid; e < SB * SB / 2; e += 256) {
                     const int r = e >> 4, c2 = (e & 15) * 2;
                     cp_async16(dst + r * SLD + c2, A + (long long)(bi * SB + r) * ld + bj * SB + c2);
@@ -90,16 +153,33 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     cp_async_wait<0>();
     __syncthreads();
 
+    // column `cb` of the tile is final: stream out L (cb..3, cb) and the inverted diagonal block
+    auto store_column = [&](int cb, int first, int nthr) {
+        for (int bi = cb; bi < 4; bi++) {
+            const double* ls = Lb + blk(bi, cb) * SBSZ;
+            const int stride = (bi == cb) ? DLD : SLD;
+            for (int e = first; e < SB * SB; e += nthr) {
+                const int r = e >> 5, c = e & 31;
+                A[(long long)(bi * SB + r) * ld + cb * SB + c] = ls[r * stride + c];
+            }
+        }
+        const double* ws = Wd + cb * SBSZ;
+        for (int e = first; e < SB * SB; e += nthr) {
+            const int r = e >> 5, c = e & 31;
+            const long long gr = cb * SB + r, gc = cb * SB + c;
+            W[gr * ldw + gc] = ws[r * SLD + c];
+            if (V) V[gr * ldv + gc] = ws[c * SLD + r];
+        }
+    };
+
     DIAG_STAMP(1);
     for (int bb = 0; bb < 4; bb++) {
-        // ---- P1 (warp 0): 32x32 Cholesky in registers ------------------------------------
+        double* Ld = Lb + blk(bb, bb) * SBSZ;        // stride DLD
         if (wid == 0) {
-            double* Ld = Lb + blk(bb, bb) * SBSZ;
-            for (int r = 0; r < SB; r++) D[r * DLD + lane] = Ld[r * SLD + lane];
-            __syncwarp();
+            // ---- P1 (warp 0): 32x32 Cholesky in registers, in place (lane = row) ---------------
             double row[SB];
 #pragma unroll
-            for (int k = 0; k < SB; k++) row[k] = D[lane * DLD + k];
+            for (int k = 0; k < SB; k++) row[k] = Ld[lane * DLD + k];
             int fail = 0;
             double myinv = 0.0;
 #pragma unroll
@@ -113,18 +193,33 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
                 const double lik = (lane == k) ? d : row[k] * id;
                 if (lane == k) myinv = id;
                 row[k] = lik;
+                if (k + 1 < SB) {
+                    // the next pivot needs only l_{k+1,k}: one shuffle keeps the serial chain short;
+                    // the rest of column k reaches the lanes through a shared-memory broadcast
+                    // (one 128-bit load per two columns instead of four shuffles)
+                    const double lnext = __shfl_sync(0xffffffffu, lik, k + 1);
+                    row[k + 1] = fma(-lik, lnext, row[k + 1]);
+                }
+                if (k + 2 < SB) {
+                    double* cb = colbuf + (k & 1) * SB;
+                    cb[lane] = lik;
+                    __syncwarp();
+                    if ((k + 2) & 1) row[k + 2] = fma(-lik, cb[k + 2], row[k + 2]);
 #pragma unroll
-                for (int j = k + 1; j < SB; j++) {
-                    const double ljk = __shfl_sync(0xffffffffu, lik, j);
-                    row[j] = fma(-lik, ljk, row[j]);
+                    for (int j = (k + 3) & ~1; j + 1 < SB; j += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(cb + j);
+                        row[j] = fma(-lik, v.x, row[j]);
+                        row[j + 1] = fma(-lik, v.y, row[j + 1]);
+                    }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < SB; k++) D[lane * DLD + k] = (k <= lane) ? row[k] : 0.0;
+            for (int k = 0; k < SB; k++) Ld[lane * DLD + k] = (k <= lane) ? row[k] : 0.0;
             invd[lane] = myinv;
             if (fail && lane == 0 && *info == 0) *info = col0 + bb * SB + fail;
-            __syncwarp();
-            for (int r = 0; r < SB; r++) Ld[r * SLD + lane] = D[r * DLD + lane];
+        } else if (bb > 0) {
+            // ---- warps 1..7 meanwhile: the previous column is final, stream it out -------------
+            store_column(bb - 1, tid - 32, 224);
         }
         __syncthreads();
         DIAG_STAMP(2 + bb * 3);
@@ -138,10 +233,10 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int k = 0; k + 1 < r; k += 2) {
-                    s0 = fma(D[r * DLD + k], w[k], s0);
-                    s1 = fma(D[r * DLD + k + 1], w[k + 1], s1);
+                    s0 = fma(Ld[r * DLD + k], w[k], s0);
+                    s1 = fma(Ld[r * DLD + k + 1], w[k + 1], s1);
                 }
-                if (r & 1) s0 = fma(D[r * DLD + r - 1], w[r - 1], s0);
+                if (r & 1) s0 = fma(Ld[r * DLD + r - 1], w[r - 1], s0);
                 w[r] = (((r == lane) ? 1.0 : 0.0) - (s0 + s1)) * invd[r];
             }
             double* Wo = Wd + bb * SBSZ;
@@ -164,10 +259,10 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int l = 0; l + 1 < c; l += 2) {
-                    s0 = fma(xr[l], D[c * DLD + l], s0);
-                    s1 = fma(xr[l + 1], D[c * DLD + l + 1], s1);
+                    s0 = fma(xr[l], Ld[c * DLD + l], s0);
+                    s1 = fma(xr[l + 1], Ld[c * DLD + l + 1], s1);
                 }
-                if (c & 1) s0 = fma(xr[c - 1], D[c * DLD + c - 1], s0);
+                if (c & 1) s0 = fma(xr[c - 1], Ld[c * DLD + c - 1], s0);
                 xr[c] = (xr[c] - (s0 + s1)) * invd[c];
             }
 #pragma unroll
@@ -178,114 +273,114 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
         __syncthreads();
         DIAG_STAMP(3 + bb * 3);
 
-        // ---- P4: trailing update A_ij -= L_ib L_jb^T, bb < j <= i, on DMMA -------------------
+        // ---- P4: trailing update A_ij -= L_ib L_jb^T, bb < j <= i, on DMMA: one 16 x 32 strip
+        //      (eight independent accumulators) per warp item ------------------------------------
         const int npairs = nbelow * (nbelow + 1) / 2;
-        for (int item = wid; item < npairs * 16; item += 8) {
-            const int pr = item >> 4, rt = (item >> 2) & 3, ct = item & 3;
+        for (int item = wid; item < npairs * 2; item += 8) {
+            const int pr = item >> 1, hf = item & 1;
             int ii = 0;
             while ((ii + 1) * (ii + 2) / 2 <= pr) ii++;
             const int jj = pr - ii * (ii + 1) / 2;
             const int bi = bb + 1 + ii, bj = bb + 1 + jj;
-            double* Cb = Lb + blk(bi, bj) * SBSZ + (rt * 8 + g) * SLD + ct * 8 + 2 * t;
-            double c0 = Cb[0], c1 = Cb[1];
-            const double* Ap = Lb + blk(bi, bb) * SBSZ + (rt * 8 + g) * SLD + t;
-            const double* Bp = Lb + blk(bj, bb) * SBSZ + (ct * 8 + g) * SLD + t;
+            double* Cb = Lb + blk(bi, bj) * SBSZ;
+            const int cs = (bi == bj) ? DLD : SLD;
+            double acc[2][4][2];
 #pragma unroll
-            for (int kk = 0; kk < 8; kk++) dmma884(c0, c1, -Ap[kk * 4], Bp[kk * 4]);
-            Cb[0] = c0;
-            Cb[1] = c1;
+            for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+                for (int ct = 0; ct < 4; ct++) {
+                    const double* p = Cb + (hf * 16 + rt * 8 + g) * cs + ct * 8 + 2 * t;
+                    acc[rt][ct][0] = p[0];
+                    acc[rt][ct][1] = p[1];
+                }
+            // B operand "col" layout: B[k][n] = L_jb[n][k]
+            const double* Ap = Lb + blk(bi, bb) * SBSZ + (hf * 16 + g) * SLD + t;
+            const double* Bp = Lb + blk(bj, bb) * SBSZ + g * SLD + t;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) {
+                double a[2], b[4];
+#pragma unroll
+                for (int rt = 0; rt < 2; rt++) a[rt] = -Ap[rt * 8 * SLD + kk * 4];
+#pragma unroll
+                for (int ct = 0; ct < 4; ct++) b[ct] = Bp[ct * 8 * SLD + kk * 4];
+#pragma unroll
+                for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+                    for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
+            }
+#pragma unroll
+            for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+                for (int ct = 0; ct < 4; ct++) {
+                    double* p = Cb + (hf * 16 + rt * 8 + g) * cs + ct * 8 + 2 * t;
+                    p[0] = acc[rt][ct][0];
+                    p[1] = acc[rt][ct][1];
+                }
         }
         __syncthreads();
         DIAG_STAMP(4 + bb * 3);
     }
 
-    // ---- L is final: stream it out (zeros above the diagonal), which also frees the four
-    //      diagonal L slots as scratch for the inverse ------------------------------------------
-    for (int bi = 0; bi < 4; bi++)
-        for (int bj = 0; bj < 4; bj++) {
-            const bool low = bi >= bj;
-            const double* ls = Lb + (low ? blk(bi, bj) : 0) * SBSZ;
-            for (int e = tid; e < SB * SB; e += 256) {
-                const int r = e >> 5, c = e & 31;
-                A[(long long)(bi * SB + r) * ld + bj * SB + c] = low ? ls[r * SLD + c] : 0.0;
-            }
-        }
-    // diagonal sub-blocks of W / V and the structural zeros of both
-    for (int bi = 0; bi < 4; bi++)
-        for (int bj = 0; bj < 4; bj++) {
-            if (bi > bj) {                       // W strictly-lower blocks come from phase 5; V's are zero
-                if (V)
-                    for (int e = tid; e < SB * SB; e += 256)
-                        V[(long long)(bi * SB + (e >> 5)) * ldv + bj * SB + (e & 31)] = 0.0;
-                continue;
-            }
-            const double* ws = Wd + bi * SBSZ;
-            for (int e = tid; e < SB * SB; e += 256) {
-                const int r = e >> 5, c = e & 31;
-                const long long gr = bi * SB + r, gc = bj * SB + c;
-                if (bi == bj) {
-                    W[gr * ldw + gc] = ws[r * SLD + c];
-                    if (V) V[gr * ldv + gc] = ws[c * SLD + r];
-                } else {
-                    W[gr * ldw + gc] = 0.0;      // W strictly-upper blocks; V's come from phase 5
-                }
-            }
-        }
+    // last column (L_33, W_33); afterwards the four diagonal L slots are scratch for the inverse
+    store_column(3, tid, 256);
     __syncthreads();
     DIAG_STAMP(14);
 
-    // ---- P5: off-diagonal sub-blocks of W = L^-1 by block distance d:
-    //      W_ij = -W_ii * S,  S = sum_{k=j}^{i-1} L_ik W_kj
-    //      slots: S(i,j) -> freed diagonal slot j;  W_10 -> diagonal slot 3, W_21 -> staging block,
-    //      W_20 -> diagonal slot 2 (the only results that later rounds read back).
-    auto wsrc = [&](int k, int j) -> const double* {
-        if (k == j) return Wd + k * SBSZ;
-        if (k == 1) return Lb + blk(3, 3) * SBSZ;              // W_10
-        if (j == 1) return D;                                  // W_21
-        return Lb + blk(2, 2) * SBSZ;                          // W_20
-    };
-    for (int d = 1; d < 4; d++) {
-        const int nj = 4 - d;
-        for (int item = wid; item < nj * 16; item += 8) {
-            const int j = item >> 4, rt = (item >> 2) & 3, ct = item & 3, i = j + d;
-            double c0 = 0.0, c1 = 0.0;
-            for (int k = j; k < i; k++) {
-                const double* Ap = Lb + blk(i, k) * SBSZ + (rt * 8 + g) * SLD + t;
-                const double* Bp = wsrc(k, j) + t * SLD + ct * 8 + g;
-#pragma unroll
-                for (int kk = 0; kk < 8; kk++) dmma884(c0, c1, Ap[kk * 4], Bp[kk * 4 * SLD]);
-            }
-            double* Sb = Lb + blk(j, j) * SBSZ + (rt * 8 + g) * SLD + ct * 8 + 2 * t;
-            Sb[0] = c0;
-            Sb[1] = c1;
-        }
-        __syncthreads();
-        for (int item = wid; item < nj * 16; item += 8) {
-            const int j = item >> 4, rt = (item >> 2) & 3, ct = item & 3, i = j + d;
-            double c0 = 0.0, c1 = 0.0;
-            const double* Wi = Wd + i * SBSZ + (rt * 8 + g) * SLD + t;
-            const double* Sp = Lb + blk(j, j) * SBSZ + t * SLD + ct * 8 + g;
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) dmma884(c0, c1, -Wi[kk * 4], Sp[kk * 4 * SLD]);
-            double* keep = nullptr;
-            if (i == 1) keep = Lb + blk(3, 3) * SBSZ;           // W_10
-            else if (i == 2 && j == 1) keep = D;                // W_21
-            else if (i == 2 && j == 0) keep = Lb + blk(2, 2) * SBSZ;   // W_20
-            const int r = rt * 8 + g, c = ct * 8 + 2 * t;
-            if (keep) {
-                keep[r * SLD + c] = c0;
-                keep[r * SLD + c + 1] = c1;
-            }
-            const long long gr = i * SB + r, gc = j * SB + c;
-            *reinterpret_cast<double2*>(W + gr * ldw + gc) = make_double2(c0, c1);
-            if (V) {
-                V[gc * ldv + gr] = c0;
-                V[(gc + 1) * ldv + gr] = c1;
-            }
-        }
-        __syncthreads();
-        DIAG_STAMP(14 + d);
+    // ---- P5: off-diagonal sub-blocks of W = L^-1 by pairwise merges (same recursion as trtri):
+    //      level 1  W_10 = -W_11 (L_10 W_00),  W_32 = -W_33 (L_32 W_22)
+    //      level 2  W[2:4,0:2] = -W[2:4,2:4] (L[2:4,0:2] W[0:2,0:2])        (64 x 64 blocks)
+    //      scratch: S_10 -> diag slot 0, S_32 -> diag slot 1, W_10 -> diag slot 2, W_32 -> diag slot 3,
+    //      then S_20, S_21 -> diag slots 0, 1 and S_30, S_31 -> the dead L_10, L_32 slots.
+    double* const dg0 = Lb + blk(0, 0) * SBSZ;
+    double* const dg1 = Lb + blk(1, 1) * SBSZ;
+    double* const W10 = Lb + blk(2, 2) * SBSZ;
+    double* const W32 = Lb + blk(3, 3) * SBSZ;
+    double acc[2][4][2];
+    if (wid < 4) {                                    // level 1a
+        const int q = wid >> 1, hf = wid & 1, i = q ? 3 : 1, j = q ? 2 : 0;
+        strip_zero(acc);
+        strip_mm(acc, Lb + blk(i, j) * SBSZ, Wd + j * SBSZ, hf, g, t, 1.0);
+        strip_to_smem(acc, q ? dg1 : dg0, hf, g, t);
     }
+    __syncthreads();
+    if (wid < 4) {                                    // level 1b
+        const int q = wid >> 1, hf = wid & 1, i = q ? 3 : 1, j = q ? 2 : 0;
+        strip_zero(acc);
+        strip_mm(acc, Wd + i * SBSZ, q ? dg1 : dg0, hf, g, t, -1.0);
+        strip_to_smem(acc, q ? W32 : W10, hf, g, t);
+        strip_to_wv(acc, W, ldw, V, ldv, i, j, hf, g, t);
+    }
+    __syncthreads();
+    DIAG_STAMP(15);
+    {                                                 // level 2a: S_ij = sum_k L_ik W_kj, k = j..1
+        const int i = 2 + (wid >> 2), j = (wid >> 1) & 1, hf = wid & 1;
+        strip_zero(acc);
+        if (j == 0) {
+            strip_mm(acc, Lb + blk(i, 0) * SBSZ, Wd, hf, g, t, 1.0);
+            strip_mm(acc, Lb + blk(i, 1) * SBSZ, W10, hf, g, t, 1.0);
+        } else {
+            strip_mm(acc, Lb + blk(i, 1) * SBSZ, Wd + SBSZ, hf, g, t, 1.0);
+        }
+        // destinations (diag slots 0/1, dead L_10 / L_32) are not read by anyone in this phase
+        double* Sdst = (i == 2) ? (j ? dg1 : dg0) : (j ? Lb + blk(3, 2) * SBSZ : Lb + blk(1, 0) * SBSZ);
+        strip_to_smem(acc, Sdst, hf, g, t);
+    }
+    __syncthreads();
+    DIAG_STAMP(16);
+    {                                                 // level 2b: W_ij = -sum_k W_ik S_kj, k = 2..i
+        const int i = 2 + (wid >> 2), j = (wid >> 1) & 1, hf = wid & 1;
+        const double* S2 = j ? dg1 : dg0;
+        const double* S3 = j ? Lb + blk(3, 2) * SBSZ : Lb + blk(1, 0) * SBSZ;
+        strip_zero(acc);
+        if (i == 2) {
+            strip_mm(acc, Wd + 2 * SBSZ, S2, hf, g, t, -1.0);
+        } else {
+            strip_mm(acc, W32, S2, hf, g, t, -1.0);
+            strip_mm(acc, Wd + 3 * SBSZ, S3, hf, g, t, -1.0);
+        }
+        strip_to_wv(acc, W, ldw, V, ldv, i, j, hf, g, t);
+    }
+    DIAG_STAMP(17);
 }
 
 // ===========================================================================
@@ -504,6 +599,21 @@ loglh_kernel(const double* L, long long n, long long ld, long long sL, const dou
     }
 }
 
+// structural zeros of the inverted diagonal blocks: W_kk strictly-upper and V_kk strictly-lower
+// 32x32 sub-blocks (one parallel launch per factorisation instead of stores on every
+// diagonal-block kernel's serial path)
+__global__ void __launch_bounds__(256) zero_diag_blocks_kernel(double* W, long long ldw, long long sW, double* V,
+                                                               long long ldv, long long sV) {
+    const long long o = (long long)blockIdx.x * GPB_NB;
+    double* Wp = W + (long long)blockIdx.y * sW + o * ldw + o;
+    double* Vp = V ? V + (long long)blockIdx.y * sV + o * ldv + o : nullptr;
+    for (int e = threadIdx.x; e < GPB_NB * GPB_NB / 2; e += 256) {
+        const int r = e >> 6, c2 = (e & 63) * 2;
+        if ((c2 >> 5) > (r >> 5)) *reinterpret_cast<double2*>(Wp + (long long)r * ldw + c2) = make_double2(0.0, 0.0);
+        if (Vp && (c2 >> 5) < (r >> 5)) *reinterpret_cast<double2*>(Vp + (long long)r * ldv + c2) = make_double2(0.0, 0.0);
+    }
+}
+
 __global__ void tril_kernel(double* A, long long n, long long ld, long long sA) {
     A += (long long)blockIdx.z * sA;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,7 +650,7 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     GPB_REQUIRE(ld >= n && ldw >= n && (!V || ldv >= n), "leading dimension too small");
     GPB_REQUIRE(A && W && info, "null pointer");
     GPB_REQUIRE(ld % 2 == 0 && ldw % 2 == 0 && (!V || ldv % 2 == 0), "leading dimensions must be even");
-    GPB_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "W must be 16-byte aligned");
+    GPB_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0, "W and V must be 16-byte aligned");
     static bool attr_set = false;
     if (!attr_set) {
         GPB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
@@ -548,6 +658,8 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     }
     GPB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
     const int T = (int)(n / GPB_NB);
+    zero_diag_blocks_kernel<<<dim3((unsigned)T, (unsigned)batch), 256, 0, st>>>(W, ldw, sW, V, ldv, sV);
+    GPB_LAUNCH_CHECK("zero_diag_blocks_kernel");
     // Two-level blocking: an outer panel of `inner` 128-columns is factored left-looking
     // (skinny column updates with K = q*128), then ONE trailing update with K = inner*128
     // touches the rest of the matrix -- half (or a quarter) as many passes over the trailing

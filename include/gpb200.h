@@ -67,8 +67,10 @@ int gpb_kernel_matvec(int kind, const double* theta, const double* x1, int64_t n
                       int nout, double* const* out, void* stream);
 
 /* ---- factorisation and solves, device pointers (n multiple of 128) ---------- */
-/* In-place lower Cholesky of the batch of n x n matrices A (strict upper part of the
- * diagonal blocks zeroed, off-diagonal upper tiles untouched -- see gpb_tril).  Also
+/* In-place lower Cholesky of the batch of n x n matrices A.  Only the lower triangle is read
+ * and written at 32-column granularity: the strict upper part of the 32x32 diagonal
+ * sub-blocks is zeroed, everything else above the diagonal is left untouched -- see
+ * gpb_tril for the dense lower-triangular matrix scipy returns.  Also
  * writes the inverted 128x128 diagonal blocks into W (lower) and, if V != NULL, their
  * transposes into V.  info[b] = 0 or first failing column + 1.
  * Replaces scipy.linalg.cholesky(lower=True) at gp/gp.py:294.                       */
@@ -184,6 +186,11 @@ int gpb_periodic_d2K_dpdp(double* out, const double* x1, int64_t n1, const doubl
  * FP64 tensor (DMMA.8x8x4) and FP64 FMA issue-rate microbenchmarks: the roofline
  * denominator for the factorisation (MEASURED_PEAKS.json has no fp64 figure).          */
 int gpb_microbench_fp64(int use_dmma, int iters, double* tflops, double* ms);
+/* Dependent-issue latencies in SM cycles, one warp: out7 = {DFMA chain, rsqrt(+DADD) chain, 64-bit
+ * shuffle chain, dependent DMMA chain, DMMA issue interval with 8 independent accumulators,
+ * 1/sqrt(+DADD) chain, shared-memory store->load round trip}.  These bound the serial paths
+ * of the diagonal-block factorisation.                                         */
+int gpb_microbench_latency(double* out7);
 /* number of kernel launches issued by this library since load (bench.py gpu_launches) */
 int64_t gpb_launch_count(void);
 /* Tuning knobs (0 = built-in default; also readable from the environment):
