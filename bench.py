@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="candidates per GPU per step")
+    ap.add_argument("--batch", type=int, default=32, help="candidates per GPU per step (17 GB workspace at N=4096)")
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-posterior", action="store_true")

@@ -44,6 +44,7 @@ _PROTOS = {
                                  _i64, c_int, c_int, vp]),
     "gpb_kernel_matvec": (c_int, [c_int, dp, vp, _i64, vp, _i64, c_int, ip, ip, dp, POINTER(vp), c_int,
                                   POINTER(vp), vp]),
+    "gpb_post_var": (c_int, [c_int, dp, vp, _i64, _i64, _i64, vp, vp]),
     "gpb_potrf": (c_int, [vp, _i64, _i64, _i64, c_int, vp, _i64, _i64, vp, _i64, _i64, vp, vp]),
     "gpb_potrs": (c_int, [vp, vp, _i64, _i64, _i64, _i64, _i64, c_int, vp, _i64, vp, vp, _i64, vp, vp]),
     "gpb_trtri": (c_int, [vp, _i64, _i64, _i64, c_int, vp, _i64, _i64, vp, _i64, _i64, vp, _i64, _i64, vp]),

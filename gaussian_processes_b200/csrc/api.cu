@@ -320,6 +320,15 @@ int gpb_kernel_matvec(int kind, const double* theta, const double* x1, int64_t n
                                    nout, out, 0, 0, S(stream));
 }
 
+int gpb_post_var(int kind, const double* theta, const double* Z, int64_t ldz, int64_t m, int64_t n,
+                 double* out, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(theta, "null pointer");
+    KParams P;
+    gpb_make_kparams(&P, kind, theta, 0.0);
+    return gpb_launch_post_var(kind, &P, Z, ldz, m, n, out, S(stream));
+}
+
 int gpb_potrf(double* A, int64_t n, int64_t ld, int64_t stride_a, int batch, double* W, int64_t ldw,
               int64_t stride_w, double* V, int64_t ldv, int64_t stride_v, int* info, void* stream) {
     return gpb_launch_potrf(A, n, ld, stride_a, batch, W, ldw, stride_w, V, ldv, stride_v, info, S(stream));

@@ -196,6 +196,46 @@ __global__ void __launch_bounds__(256) fused_matvec_kernel(const MatvecArgs a) {
     }
 }
 
+// Posterior-mean fast path (gp.py:597, one pair: slice 0, coefficient 1): the slice is a
+// compile-time constant, a warp owns two rows so every x2 / vector load feeds two kernel
+// evaluations, and lanes take two adjacent columns per 128-bit load.
+template <int KIND>
+__global__ void __launch_bounds__(256) mean_kernel(const MatvecArgs a) {
+    __shared__ KParams sP;
+    load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double* vec = a.vec[0] + (long long)blockIdx.z * a.vstride;
+    double* out = a.out[0] + (long long)blockIdx.z * a.ostride;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(a.x2) | reinterpret_cast<uintptr_t>(vec)) & 15) == 0;
+    const long long n2v = vec_ok ? (a.n2 & ~1LL) : 0;
+    for (long long r0 = ((long long)blockIdx.x * 8 + wid) * 2; r0 < a.n1; r0 += (long long)gridDim.x * 16) {
+        const bool two = r0 + 1 < a.n1;
+        const double xa = a.x1[r0], xb = two ? a.x1[r0 + 1] : xa;
+        double acc_a = 0.0, acc_b = 0.0;
+        for (long long c = 2 * lane; c < n2v; c += 64) {
+            const double2 xc = *reinterpret_cast<const double2*>(a.x2 + c);
+            const double2 vc = *reinterpret_cast<const double2*>(vec + c);
+            double u[10];
+            gpb_eval_unique<KIND>(sP, xa - xc.x, 1u, u); acc_a = fma(u[0], vc.x, acc_a);
+            gpb_eval_unique<KIND>(sP, xa - xc.y, 1u, u); acc_a = fma(u[0], vc.y, acc_a);
+            gpb_eval_unique<KIND>(sP, xb - xc.x, 1u, u); acc_b = fma(u[0], vc.x, acc_b);
+            gpb_eval_unique<KIND>(sP, xb - xc.y, 1u, u); acc_b = fma(u[0], vc.y, acc_b);
+        }
+        for (long long c = n2v + lane; c < a.n2; c += 32) {
+            double u[10];
+            const double xc = a.x2[c], vc = vec[c];
+            gpb_eval_unique<KIND>(sP, xa - xc, 1u, u); acc_a = fma(u[0], vc, acc_a);
+            gpb_eval_unique<KIND>(sP, xb - xc, 1u, u); acc_b = fma(u[0], vc, acc_b);
+        }
+        acc_a = warp_sum(acc_a);
+        acc_b = warp_sum(acc_b);
+        if (lane == 0) {
+            out[r0] = acc_a;
+            if (two) out[r0 + 1] = acc_b;
+        }
+    }
+}
+
 int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int batch,
                             const double* x1, long long n1, const double* x2, long long n2,
                             int npairs, const int* slice, const int* outidx, const double* coef,
@@ -220,7 +260,13 @@ int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int b
     if (nb > 148 * 16) nb = 148 * 16;
     dim3 grid((unsigned)nb, 1, (unsigned)batch);
     GpbProfScope prof(GPB_KC_BUILD, st);
-    if (kind == GPB_GAUSSIAN) fused_matvec_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
+    if (npairs == 1 && nout == 1 && slice[0] == 0 && coef[0] == 1.0) {
+        long long nbm = (n1 + 15) / 16;
+        if (nbm > 148 * 16) nbm = 148 * 16;
+        const dim3 gm((unsigned)nbm, 1, (unsigned)batch);
+        if (kind == GPB_GAUSSIAN) mean_kernel<GPB_GAUSSIAN><<<gm, 256, 0, st>>>(a);
+        else mean_kernel<GPB_PERIODIC><<<gm, 256, 0, st>>>(a);
+    } else if (kind == GPB_GAUSSIAN) fused_matvec_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
     else fused_matvec_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
     GPB_LAUNCH_CHECK("fused_matvec_kernel");
     return GPB_OK;
@@ -431,5 +477,45 @@ int gpb_launch_grad_reduce(int kind, const KParams* P, const KParams* Pb, int ba
     GPB_LAUNCH_CHECK("grad_reduce_kernel");
     sum_partials_kernel<<<batch, 256, 0, st>>>(partial, nb, GPB_RED_WIDTH, out16);
     GPB_LAUNCH_CHECK("sum_partials_kernel");
+    return GPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 4. predictive variance: var[r] = K(xo_r, xo_r) - sum_c Z[r][c]^2 with Z = K(xo, x) L^-T, i.e.
+//    diag(GP.cov) (gp.py:625, what GP.plot needs, gp.py:692-693) without the M x M matrix.
+// ---------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) post_var_kernel(const KParams P, const double* Z, long long ldz, long long m,
+                                                       long long n, double* out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double u[10];
+    gpb_eval_unique<KIND>(P, 0.0, 1u, u);        // k(x*, x*): both kernels are stationary
+    const double k0 = u[0];
+    for (long long r = (long long)blockIdx.x * 8 + wid; r < m; r += (long long)gridDim.x * 8) {
+        const double* zr = Z + r * ldz;
+        double s0 = 0.0, s1 = 0.0;
+        const long long nv = ((reinterpret_cast<uintptr_t>(zr) & 15) == 0) ? (n & ~1LL) : 0;
+        for (long long c = 2 * lane; c < nv; c += 64) {
+            const double2 v = *reinterpret_cast<const double2*>(zr + c);
+            s0 = fma(v.x, v.x, s0);
+            s1 = fma(v.y, v.y, s1);
+        }
+        for (long long c = nv + lane; c < n; c += 32) s0 = fma(zr[c], zr[c], s0);
+        const double s = warp_sum(s0 + s1);
+        if (lane == 0) out[r] = k0 - s;
+    }
+}
+
+int gpb_launch_post_var(int kind, const KParams* P, const double* Z, long long ldz, long long m, long long n,
+                        double* out, cudaStream_t st) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(Z && out && ldz >= n, "bad argument");
+    if (m == 0) return GPB_OK;
+    long long nb = (m + 7) / 8;
+    if (nb > 148 * 8) nb = 148 * 8;
+    GpbProfScope prof(GPB_KC_REDUCE, st);
+    if (kind == GPB_GAUSSIAN) post_var_kernel<GPB_GAUSSIAN><<<(unsigned)nb, 256, 0, st>>>(*P, Z, ldz, m, n, out);
+    else post_var_kernel<GPB_PERIODIC><<<(unsigned)nb, 256, 0, st>>>(*P, Z, ldz, m, n, out);
+    GPB_LAUNCH_CHECK("post_var_kernel");
     return GPB_OK;
 }

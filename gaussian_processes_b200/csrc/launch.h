@@ -55,6 +55,9 @@ int gpb_launch_grad_reduce(int kind, const KParams* P, const KParams* Pb, int ba
                            const double* alpha, long long astride, int nsl, const int* slices,
                            double* partial, double* out16, cudaStream_t st);
 
+int gpb_launch_post_var(int kind, const KParams* P, const double* Z, long long ldz, long long m, long long n,
+                        double* out, cudaStream_t st);
+
 // potrf.cu
 int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,

@@ -333,6 +333,26 @@ class Engine(object):
                 yield r0, r1
         return self._rows_out(C, m, m, blocks(), host)
 
+    def var(self, xo):
+        """diag(cov(xo)) = k(x*, x*) - |K(x*, x) L^-T|^2 row by row: N^2 M flop instead of
+        N^2 M + N M^2, and M doubles back to the host instead of M^2 (additive API)."""
+        W, _ = self.inv_factor()
+        m = int(xo.size)
+        if m == 0:
+            return np.empty(0, dtype=DTYPE)
+        out = D.empty(m)
+        dxo = D.to_device(xo)
+        step = max(D.NB, (1 << 28) // self.npad // D.NB * D.NB)      # <= 2 GiB of Z at a time
+        for lo in range(0, m, step):
+            hi = min(m, lo + step)
+            mp = D.roundup(hi - lo)
+            Kxox = self.build(dxo[lo:hi], hi - lo, self.dx, self.n, mp, self.npad, 1)[0]
+            Z = D.empty(mp, self.npad)
+            self.gemm(Kxox, W, Z, mp, self.npad, self.npad, b_tri=1)
+            call("gpb_post_var", self.kind, self._theta(), D.ptr(Z), self.npad, hi - lo, self.n,
+                 out[lo:].data_ptr(), D.stream_ptr())
+        return D.to_host(out).copy()
+
     def cov_rows(self, xo, lo, hi, host=True):
         """Rows lo:hi of cov(xo) -- the unit of test-point sharding: needs no peer
         data.  U = K(xo_r, x) Ki, then K(xo_r, xo) - U K(xo, x)^T; 2 N^2 m_r + 2 N M m_r flop.

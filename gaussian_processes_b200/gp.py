@@ -325,6 +325,11 @@ class GP(object):
         r"""Predictive covariance (Eq. 2.24 of R&W), :math:`m\times m`."""
         return self._engine().cov(np.asarray(xo, dtype=DTYPE))
 
+    def var(self, xo):
+        r"""Predictive variance, the diagonal of ``cov(xo)``, without forming the :math:`m\times m`
+        matrix (additive API; what ``plot`` draws)."""
+        return self._engine().var(np.asarray(xo, dtype=DTYPE))
+
     def cov_rows(self, xo, lo, hi):
         r"""Rows ``lo:hi`` of ``cov(xo)`` (:math:`(hi-lo)\times m`): the shard one GPU owns when
         test points are partitioned across devices (additive API)."""
@@ -344,7 +349,7 @@ class GP(object):
             xlim = (x.min(), x.max())
         X = np.linspace(xlim[0], xlim[1], 1000)
         mean = self.mean(X)
-        std = np.sqrt(np.diag(self.cov(X)))
+        std = np.sqrt(self.var(X))
         ax.fill_between(X, mean - std, mean + std, color=color, alpha=0.3)
         ax.plot(X, mean, lw=2, color=color)
         ax.plot(x, y, "o", ms=5, color=markercolor)

@@ -17,24 +17,31 @@ import numpy as np
 
 from . import engine as _engine
 
-__all__ = ["fit_MLII", "batch_eval", "shard_bounds", "select_best", "MLIIResult"]
+__all__ = ["fit_MLII", "batch_eval", "shard_bounds", "select_best", "MLIIResult", "refine"]
 
 
 class MLIIResult(object):
     """Outcome of a batched search."""
 
-    def __init__(self, best_index, candidates, log_lh, dloglh):
+    def __init__(self, best_index, candidates, log_lh, dloglh, refined=None):
         self.best_index = int(best_index)
         self.candidates = candidates
         self.log_lh = log_lh
         self.dloglh_dtheta = dloglh
+        #: None, or dict(params [R, n_theta], log_lh [R], dloglh_dtheta [R, n_theta], start_index [R],
+        #: best (row of the winner), evals (candidate evaluations spent)) from the gradient refinement
+        self.refined = refined
 
     @property
     def best_params(self):
+        if self.refined is not None:
+            return self.refined["params"][self.refined["best"]].copy()
         return self.candidates[self.best_index].copy()
 
     @property
     def best_log_lh(self):
+        if self.refined is not None:
+            return self.refined["log_lh"][self.refined["best"]]
         return self.log_lh[self.best_index]
 
 
@@ -89,7 +96,80 @@ def _gather_rows(local, counts, group=None):
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
 
 
-def fit_MLII(gp, candidates, distributed=None, group=None, set_params=True, evaluate=None):
+def refine(starts, evaluate_np, steps=20, gtol=1e-6, max_halvings=8):
+    """Batched BFGS ascent on log p(y | x, theta) from several starting points at once.
+
+    Every round evaluates ONE trial point per restart in a single batched device call, so R
+    restarts cost the same number of launches as one.  The search runs in u = log(theta)
+    (all parameters must stay positive: h, w, p >= EPS, s > 0), with an Armijo backtracking
+    line search per restart; a restart whose trial is not PD (log_lh = -inf / NaN) simply
+    backtracks.  Restarts stop individually when |d log_lh / du|_inf <= gtol.
+
+    starts      : [R, n_theta] strictly positive parameter rows
+    evaluate_np : f(thetas [b, n_theta]) -> (log_lh [b], dloglh_dtheta [b, n_theta]) numpy
+    Returns (theta [R, n_theta], log_lh [R], dloglh_dtheta [R, n_theta], n_evals).
+    """
+    th = np.array(starts, dtype=np.float64, copy=True)
+    R, nth = th.shape
+    if R == 0:
+        return th, np.empty(0), np.empty((0, nth)), 0
+    if np.any(th <= 0):
+        raise ValueError("refine: parameters must be strictly positive (search runs in log space)")
+    u = np.log(th)
+    f, g = evaluate_np(th)
+    f = np.where(np.isnan(f), -np.inf, f)
+    n_evals = R
+    gu = g * th                                     # d f / d u = theta * d f / d theta
+    H = np.tile(np.eye(nth), (R, 1, 1))             # inverse-Hessian estimates of -f
+    active = np.isfinite(f) & np.all(np.isfinite(gu), axis=1)
+    for _ in range(int(steps)):
+        active &= np.max(np.abs(gu), axis=1) > gtol
+        if not active.any():
+            break
+        d = np.einsum("rij,rj->ri", H, gu)          # ascent direction
+        slope = np.einsum("ri,ri->r", d, gu)
+        bad = ~(slope > 0)                          # lost positive-definiteness: restart from steepest ascent
+        H[bad] = np.eye(nth)
+        d[bad] = gu[bad]
+        slope[bad] = np.einsum("ri,ri->r", gu[bad], gu[bad])
+        # first trial: unit quasi-Newton step, clipped to a factor e^2 per parameter
+        alpha = np.minimum(1.0, 2.0 / np.maximum(np.max(np.abs(d), axis=1), 1e-300))
+        pending = active.copy()
+        u_new, f_new, g_new = u.copy(), f.copy(), g.copy()
+        for _h in range(int(max_halvings)):
+            idx = np.nonzero(pending)[0]
+            if idx.size == 0:
+                break
+            ut = u[idx] + alpha[idx, None] * d[idx]
+            ft, gt = evaluate_np(np.exp(ut))
+            n_evals += idx.size
+            ft = np.where(np.isnan(ft), -np.inf, ft)
+            ok = ft >= f[idx] + 1e-4 * alpha[idx] * slope[idx]
+            ok &= np.all(np.isfinite(gt), axis=1)
+            acc = idx[ok]
+            u_new[acc], f_new[acc], g_new[acc] = ut[ok], ft[ok], gt[ok]
+            pending[acc] = False
+            alpha[idx[~ok]] *= 0.5
+        moved = active & ~pending
+        active &= ~pending                          # line search failed: this restart is done
+        if moved.any():
+            th_new = np.exp(u_new)
+            gu_new = g_new * th_new
+            sk = u_new - u
+            yk = -(gu_new - gu)                     # gradient difference of -f
+            for r in np.nonzero(moved)[0]:
+                sy = float(sk[r] @ yk[r])
+                if sy > 1e-12 * float(np.linalg.norm(sk[r]) * np.linalg.norm(yk[r])):
+                    rho = 1.0 / sy
+                    I = np.eye(nth)
+                    V = I - rho * np.outer(sk[r], yk[r])
+                    H[r] = V @ H[r] @ V.T + rho * np.outer(sk[r], sk[r])
+            u[moved], f[moved], g[moved], gu[moved] = u_new[moved], f_new[moved], g_new[moved], gu_new[moved]
+    return np.exp(u), f, g, n_evals
+
+
+def fit_MLII(gp, candidates, distributed=None, group=None, set_params=True, evaluate=None,
+             refine_top=0, refine_steps=20, refine_gtol=1e-6):
     """Pick the candidate parameter vector with the largest marginal log likelihood.
 
     candidates : [B, n_theta] array, rows ordered like ``gp.params`` (identical on every
@@ -98,6 +178,10 @@ def fit_MLII(gp, candidates, distributed=None, group=None, set_params=True, eval
     evaluate : optional ``f(thetas) -> torch tensor [b, 2 + n_theta]`` (log_lh, grad...,
         info); defaults to the CUDA evaluator.  Exists so the sharding logic can be
         exercised on CPU (gloo) without a GPU.
+    refine_top : R > 0 -> after the search, the R best candidates are polished by batched BFGS
+        ascent on their gradients (:func:`refine`; at most ``refine_steps`` iterations, stopping at
+        ``refine_gtol``).  Distributed: rank r refines starts r, r+G, ... and one more all-gather
+        assembles the refined rows.  The winner is the best refined point.
     Returns an :class:`MLIIResult`; with ``set_params`` the GP is moved to the winner.
     """
     import torch
@@ -132,7 +216,37 @@ def fit_MLII(gp, candidates, distributed=None, group=None, set_params=True, eval
     table = table.detach().cpu().numpy()
     llh, grad = table[:, 0].copy(), table[:, 1:1 + nth].copy()
     best = select_best(llh)
-    res = MLIIResult(best, cand, llh, grad)
+    refined = None
+    if refine_top and refine_top > 0:
+        order = np.argsort(-np.where(np.isnan(llh), -np.inf, llh), kind="stable")
+        order = order[np.isfinite(llh[order])][:int(refine_top)]
+
+        def evaluate_np(th):
+            t = evaluate(np.ascontiguousarray(th)).detach().cpu().numpy()
+            return t[:, 0].copy(), t[:, 1:1 + nth].copy()
+        if distributed:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            mine = order[rank::world]
+        else:
+            world, rank, mine = 1, 0, order
+        th_r, f_r, g_r, n_ev = refine(cand[mine], evaluate_np, steps=refine_steps, gtol=refine_gtol)
+        rows = np.concatenate([th_r, f_r[:, None], g_r, mine[:, None].astype(np.float64),
+                               np.full((mine.size, 1), float(n_ev))], axis=1).reshape(mine.size, 2 * nth + 3)
+        if distributed:
+            import torch.distributed as dist
+            dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+            counts = [len(order[r::world]) for r in range(world)]
+            rows = _gather_rows(torch.from_numpy(rows).to(dev), counts, group).cpu().numpy()
+        if rows.shape[0]:
+            refined = dict(params=rows[:, :nth].copy(), log_lh=rows[:, nth].copy(),
+                           dloglh_dtheta=rows[:, nth + 1:2 * nth + 1].copy(),
+                           start_index=rows[:, 2 * nth + 1].astype(np.int64),
+                           evals=int(rows[:, 2 * nth + 2].max() if distributed else n_ev))
+            refined["best"] = select_best(refined["log_lh"])
+            if not refined["log_lh"][refined["best"]] >= llh[best]:
+                refined = None                       # never return something worse than the search
+    res = MLIIResult(best, cand, llh, grad, refined)
     if set_params:
-        gp.params = cand[best]
+        gp.params = res.best_params
     return res

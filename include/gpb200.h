@@ -66,6 +66,11 @@ int gpb_kernel_matvec(int kind, const double* theta, const double* x1, int64_t n
                       const int* outidx, const double* coef, const double* const* vec,
                       int nout, double* const* out, void* stream);
 
+/* var[r] = k(x*_r, x*_r) - sum_c Z[r][c]^2 for Z = K(xo, x) L^-T (m x n, row stride ldz): the
+ * diagonal of GP.cov (gp.py:625) -- all GP.plot needs (gp.py:692-693) -- without the m x m matrix. */
+int gpb_post_var(int kind, const double* theta, const double* Z, int64_t ldz, int64_t m, int64_t n,
+                 double* out, void* stream);
+
 /* ---- factorisation and solves, device pointers (n multiple of 128) ---------- */
 /* In-place lower Cholesky of the batch of n x n matrices A.  Only the lower triangle is read
  * and written at 32-column granularity: the strict upper part of the 32x32 diagonal

@@ -170,3 +170,32 @@ def test_install_as_gp():
         for k in [k for k in sys.modules if k == "gp" or k.startswith("gp.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_refine_batched_bfgs_on_analytic_surface():
+    """mlii.refine: every restart converges to the maximiser of a concave (in log space) surface,
+    infeasible trials (log_lh = -inf, NaN gradient) only shorten the step."""
+    from gaussian_processes_b200 import mlii
+    opt = np.array([1.3, 0.4, 0.9])
+    A = np.array([[2, 0.3, 0], [0.3, 1, 0.2], [0, 0.2, 3.0]])
+    ncalls = []
+
+    def ev(th):
+        ncalls.append(len(th))
+        u = np.log(th) - np.log(opt)
+        f = -0.5 * np.einsum("bi,ij,bj->b", u, A, u) - 0.1 * np.sum(u ** 4, axis=1)
+        gu = -(u @ A) - 0.4 * u ** 3
+        g = gu / th
+        bad = th[:, 0] > 1.9                      # a "not positive definite" region
+        f = np.where(bad, -np.inf, f)
+        g[bad] = np.nan
+        return f, g
+    starts = np.array([[1.0, 1.0, 1.0], [1.8, 0.2, 0.5], [0.7, 0.9, 2.0]])
+    th, f, g, n = mlii.refine(starts, ev, steps=40, gtol=1e-9)
+    assert np.allclose(th, opt, rtol=1e-6)
+    assert np.all(f > -1e-12) and n == sum(ncalls)
+    assert max(ncalls) <= 3                      # one trial per restart per round
+    with pytest.raises(ValueError):
+        mlii.refine(np.array([[1.0, -1.0, 1.0]]), ev)
+    th0, f0, g0, n0 = mlii.refine(np.empty((0, 3)), ev)
+    assert th0.shape == (0, 3) and n0 == 0

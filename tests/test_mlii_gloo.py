@@ -36,8 +36,14 @@ def _worker(rank, world, port, B, outdir):
         return torch.tensor(rows, dtype=torch.float64)
     gp = gpb.GP(gpb.GaussianKernel(1.0, 1.0), x, y, s=1.0)
     res = gpb.fit_MLII(gp, cand, evaluate=evaluate)
+    params_search = gp.params
+    nsearch = list(calls)
+    # the same search followed by the batched BFGS polish of the 3 best candidates (starts shard over ranks)
+    res2 = gpb.fit_MLII(gp, cand, evaluate=evaluate, refine_top=3, refine_steps=25, refine_gtol=1e-7)
     np.savez(os.path.join(outdir, "r%d.npz" % rank), best=res.best_index, llh=res.log_lh,
-             grad=res.dloglh_dtheta, params=gp.params, ncalls=np.array(calls), cand=cand)
+             grad=res.dloglh_dtheta, params=params_search, ncalls=np.array(nsearch), cand=cand,
+             ref_params=res2.refined["params"], ref_llh=res2.refined["log_lh"], ref_grad=res2.refined["dloglh_dtheta"],
+             ref_start=res2.refined["start_index"], ref_best=res2.refined["best"], params2=gp.params)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,3 +64,14 @@ def test_fit_mlii_world2_gloo(tmp_path, B):
     # each rank evaluated only its shard
     assert int(r0["ncalls"].sum()) + int(r1["ncalls"].sum()) == B
     assert abs(int(r0["ncalls"].sum()) - int(r1["ncalls"].sum())) <= 1
+    # refinement: both ranks hold the same refined table; starts are the 3 best of the search; every
+    # refined point is at least as good as its start and (nearly) stationary in log-parameters
+    for k in ("ref_params", "ref_llh", "ref_grad", "ref_start", "params2"):
+        assert np.array_equal(r0[k], r1[k]), k
+    top3 = np.argsort(-llh, kind="stable")[:3]
+    assert sorted(r0["ref_start"].tolist()) == sorted(top3.tolist())
+    assert np.all(r0["ref_llh"] >= llh[r0["ref_start"]] - 1e-12)
+    assert np.max(np.abs(r0["ref_grad"] * r0["ref_params"])) < 1e-4
+    assert np.array_equal(r0["params2"], r0["ref_params"][int(r0["ref_best"])])
+    o = oracle.OracleGP(oracle.GAUSSIAN, r0["params2"][:-1], x, y, r0["params2"][-1])
+    assert abs(float(o.log_lh) - r0["ref_llh"][int(r0["ref_best"])]) <= 1e-9 * abs(float(o.log_lh))

@@ -322,3 +322,46 @@ def test_clamp_candidates_in_batch(oracle):
         if np.isfinite(o.log_lh):
             assert_parity(llh[b], o.log_lh, 1e-8)
     assert (llh == -np.inf).any() and np.isfinite(grad).all()
+
+
+# ------------------------------------------------------------------ additive APIs of this round
+@pytest.mark.parametrize("kparams,n,m", [((1.0, 0.5), 300, 257), ((1.0, 1.0, 1.3), 131, 64), ((0.8, 0.3), 64, 1)])
+def test_var_is_cov_diagonal(oracle, kparams, n, m):
+    """GP.var (fused row norms of K(xo,x) L^-T) against the oracle's explicit-inverse cov diagonal,
+    and the mean fast path (two rows per warp, 128-bit loads) at odd sizes."""
+    x, y = synth_xy(n, 21)
+    xo = np.linspace(-7, 7, m)
+    gp = GP(make_kernel(kparams), x, y, s=0.7)
+    o = oracle.OracleGP(kind_of(oracle, kparams), kparams, x, y, 0.7)
+    ocov = o.cov(xo)
+    v = gp.var(xo)
+    assert v.shape == (m,)
+    assert np.max(np.abs(v - np.diag(ocov))) <= RTOL * np.max(np.abs(ocov))
+    assert_parity(gp.mean(xo), o.mean(xo))
+    assert gp.var(np.empty(0)).shape == (0,)
+
+
+def test_fit_mlii_refine_reaches_scipy_optimum(oracle):
+    """Batched BFGS polish: from the best grid candidates the refined point is stationary, not worse
+    than any start, and agrees with scipy's optimum of the ORACLE's log_lh (same surface)."""
+    from scipy.optimize import minimize
+    x, y = synth_xy(96, 5)
+    rng = np.random.RandomState(3)
+    B = 32
+    cand = np.stack([rng.uniform(0.5, 2, B), rng.uniform(0.2, 1.5, B), rng.uniform(0.05, 0.8, B)], axis=1)
+    gp = GP(GaussianKernel(1.0, 1.0), x, y, s=1.0)
+    res = gp.fit_MLII(cand, refine_top=4, refine_steps=40, refine_gtol=1e-7)
+    assert res.refined is not None and res.refined["params"].shape == (4, 3)
+    assert res.best_log_lh >= res.log_lh[res.best_index]
+    assert np.array_equal(gp.params, res.best_params)
+    b = res.refined["best"]
+    assert np.max(np.abs(res.refined["dloglh_dtheta"][b] * res.refined["params"][b])) < 1e-5
+    o = oracle.OracleGP(oracle.GAUSSIAN, res.best_params[:2], x, y, res.best_params[2])
+    assert_parity(res.best_log_lh, o.log_lh)
+
+    def neg(u):
+        t = np.exp(u)
+        og = oracle.OracleGP(oracle.GAUSSIAN, t[:2], x, y, t[2])
+        return -float(og.log_lh), -(og.dloglh_dtheta * t)
+    ref = minimize(neg, np.log(cand[res.best_index]), jac=True, method="L-BFGS-B", options=dict(gtol=1e-8, maxiter=200))
+    assert res.best_log_lh >= -ref.fun - 1e-6 * abs(ref.fun)
