@@ -306,7 +306,19 @@ gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, co
     // ===== consumer warps =====
     const int wm = wid >> 2, wn = wid & 3;
     const int g = lane >> 2, t = lane & 3;
-    const bool skip_mma = (diag_sub == 0) && (wn >= 2);
+    // Triangular structure below the tile level: a warp tile (32 x 32) strictly above the diagonal of a
+    // lower-only diagonal block is never needed (its mirror image is computed), and triangular operands
+    // shorten the k-range of each warp individually.  Skipping warps still walk the barriers; their DMMA
+    // slots go to the other warps of the SM.
+    const int row0_w = m0 + wm * 32, col0_w = n0 + wn * 32;
+    const bool in_diag = p.lower_only && diag_tile && (BM == 64);
+    const bool skip_mma = in_diag && (col0_w > row0_w);
+    int kb_w = kbeg, ke_w = kend;
+    if (p.a_tri == 1) ke_w = min(ke_w, row0_w + 32 + p.a_off);
+    else if (p.a_tri == 2) kb_w = max(kb_w, row0_w + p.a_off);
+    if (p.b_tri == 1) ke_w = min(ke_w, col0_w + 32 + p.b_off);
+    else if (p.b_tri == 2) kb_w = max(kb_w, col0_w + p.b_off);
+    const int kt_lo = max(kb_w - kbeg, 0) / BK, kt_hi = min((max(ke_w - kbeg, 0) + BK - 1) / BK, nk);
 
     double acc[4][4][2];
 #pragma unroll
@@ -323,7 +335,7 @@ gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, co
     for (int kt = 0; kt < nk; kt++) {
         const int s = kt % STAGES;
         mbar_wait(bar_full + s * 8, (unsigned)(kt / STAGES) & 1u);
-        if (!skip_mma) {
+        if (!skip_mma && kt >= kt_lo && kt < kt_hi) {
             const unsigned char* sa = tiles + s * Cfg::STAGE_BYTES + a_row;
             const unsigned char* sb = tiles + s * Cfg::STAGE_BYTES + b_row;
 #pragma unroll
@@ -346,8 +358,11 @@ gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, co
     // ---- epilogue (registers -> global, optional mirrored store) ------------------------------
     double* C = p.C + bz * p.sC + bt * p.tC;
     double* Ct = p.Ct ? p.Ct + bz * p.sCt + bt * p.tCt : nullptr;
+    // mirrored store: off-diagonal tiles always; inside a lower-only diagonal block every warp tile strictly
+    // below the diagonal is mirrored into the skipped one above it, the diagonal warp tiles only when the
+    // mirror is a different matrix
     bool mirror = (Ct != nullptr) && !(p.lower_only && diag_tile && Ct == C);
-    if (Ct != nullptr && diag_sub == 1 && wn < 2) mirror = true;
+    if (Ct != nullptr && in_diag && col0_w < row0_w) mirror = true;
     if (skip_mma) return;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
