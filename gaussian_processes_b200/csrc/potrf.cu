@@ -22,11 +22,11 @@ namespace {
 // diagonal-block kernel: one CTA factors and inverts one 128 x 128 block held in
 // shared memory as ten 32 x 32 sub-blocks (lower block-triangle).
 //
-// Resource shape is part of the design: 138.5 KB of shared memory and <= 128 registers
-// x 256 threads, so that a diagonal-block CTA can be placed on an SM next to ONE resident
-// 64x128 GEMM CTA (92 KB, half the register file) of another candidate group instead of
-// waiting for a completely idle SM -- this is what lets the serial part of one group's
-// factorisation overlap the trailing updates of the others.
+// Resource shape is part of the design: 126.75 KB of shared memory and <= 128 registers
+// x 256 threads, so that a diagonal-block CTA fits on an SM next to ONE resident 64x128 TMA
+// GEMM CTA (97 KB, 288 x 96 registers) of another candidate group instead of waiting for a
+// completely idle SM -- this is what lets the serial part of one group's factorisation overlap
+// the trailing updates of the others.  (Stream priorities for this kernel were measured: no gain.)
 //
 // Per 32-column step bb:
 //   P1  warp 0        Cholesky of the 32x32 diagonal sub-block in registers (lane = row,
@@ -41,7 +41,7 @@ constexpr int SLD = 36;           // padded stride: 36 = 4 (mod 16) -> conflict-
 constexpr int SBSZ = SB * SLD;
 constexpr int NBLK = 10;
 constexpr int DLD = 33;           // odd stride for lane-per-row accesses
-constexpr int DIAG_SMEM = ((NBLK + 4 + 1) * SBSZ + SB + 2 * SB) * 8;   // L blocks, diagonal inverses, spare, 1/diag, column broadcast
+constexpr int DIAG_SMEM = ((NBLK + 4) * SBSZ + SB + 2 * SB) * 8;   // L blocks, diagonal inverses, 1/diag, column broadcast (126.75 KB)
 
 __device__ __forceinline__ int blk(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
 
@@ -117,8 +117,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     double* Lb = sm;                          // 10 lower sub-blocks of the tile: off-diagonal ones with stride
                                               // SLD (DMMA fragments), diagonal ones with stride DLD (lane = row)
     double* Wd = sm + NBLK * SBSZ;            // inverses of the 4 diagonal sub-blocks (stride SLD)
-    double* D = Wd + 4 * SBSZ;                // spare block
-    double* invd = D + SBSZ;
+    double* invd = Wd + 4 * SBSZ;
     double* colbuf = invd + SB;               // 2 x 32: column k of the 32x32 factor, broadcast to all lanes
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
     A += (long long)blockIdx.x * sA;
