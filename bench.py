@@ -256,13 +256,13 @@ def run_ours(args):
         gemm_launches = max(classes["gemm_nt(DMMA)"]["launches_per_step"], 1)
         flops_step = B * float(n) ** 3            # N^3/3 potrf + 2N^3/3 inverse per eval
         achieved = flops_step / (gemm_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA.8x8x4)",
+        roof = {"bound": "tensor", "kernel": "gemm_nt_tma_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the gemm_nt launches of one step, from
-                # the ncu pass committed as profiles/r01_launches_one_step_b16_dram.csv
-                # (18.60 GB over 73 launches at B=16 -> 15.93 MB per launch per candidate)
-                "traffic": 15.93e6 * B,
-                "traffic_source": "ncu dram bytes, profiles/r01_launches_one_step_b16_dram.csv (per launch, scaled by B/16)",
+                # the ncu pass committed as profiles/r01_launches_one_step_b32.csv
+                # (38.76 GB over 73 launches at B=32 -> 16.59 MB per launch per candidate)
+                "traffic": 16.59e6 * B,
+                "traffic_source": "ncu dram bytes, profiles/r01_launches_one_step_b32.csv (per launch, scaled by B/32)",
                 "algorithmic_flops_per_launch": flops_step / gemm_launches,
                 "avg_launch_ms": gemm_ms / gemm_launches, "launches_per_step": gemm_launches,
                 "peak_source": "measured live: gpb_microbench_fp64 (DMMA.8x8x4 issue rate, 148x8 CTAs); "

@@ -221,26 +221,40 @@ class Engine(object):
         bs_ci = [self.dot(a, C[i], n) for i in range(n_p)]           # alpha . c_i
         bj_kia = [self.dot(B[j], Kia, n) for j in range(n_p)]        # b_j . Ki alpha
         a_kia = self.dot(a, Kia, n)
-        # P_i = Ki dK_i (dense products on the DMMA GEMM), then traces of products
-        J = self.build(self.dx, n, self.dx, n, npad, npad, sum(1 << q for q in sl))
-        P = D.empty(n_p, npad, npad)
-        for i in range(n_p):
-            self.gemm(Ki, J[i], P[i], npad, npad, npad)
+        # P_i = Ki dK_i (dense products on the DMMA GEMM), then traces of products.  The h-slice of
+        # both kernels is proportional to K itself (dK_h = (2/h) K, gaussian_c.pyx:60-69,
+        # periodic_c.pyx:65), so P_h = (2/h) (I - s^2 Ki) needs no product: its traces follow from
+        # tr Ki, tr Ki Ki, tr P_j and tr Ki P_j.
+        ch = 2.0 / self.kparams[0]
+        dense = list(range(1, n_p))                        # parameter indices that need a real product
+        J = self.build(self.dx, n, self.dx, n, npad, npad, sum(1 << sl[i] for i in dense))
+        P = D.empty(len(dense), npad, npad)
+        for q, i in enumerate(dense):
+            self.gemm(Ki, J[q], P[q], npad, npad, npad)
         tp = D.empty(nth * nth + 1)
         part = self._partial()
 
         def trace_prod(A, Bm, slot):
             call("gpb_trace_prod", D.ptr(A), npad, D.ptr(Bm), npad, n, D.ptr(part), tp[slot:].data_ptr(), st)
-        for i in range(n_p):
-            for j in range(n_p):
-                trace_prod(P[j], P[i], i * nth + j)
-            trace_prod(Ki, P[i], i * nth + n_p)
+        tp.zero_()
+        for qi, i in enumerate(dense):
+            for qj, j in enumerate(dense):
+                trace_prod(P[qj], P[qi], i * nth + j)
+            trace_prod(Ki, P[qi], i * nth + n_p)
         trace_prod(Ki, Ki, nth * nth - 1)
+        _, t1g = self.grad_terms()                         # t1g[j] = tr(Ki dK_j) = tr P_j
         # Hessian slices: alpha^T H alpha and sum(Ki o H)
         pairs = [(i, j) for i in range(n_p) for j in range(i, n_p)]
         q0, q1, tr, aa = self.slice_reduce([hess_slice(self.kind, i, j) for i, j in pairs])
         Gh = D.to_host(Gd)
-        tph = D.to_host(tp)
+        tph = D.to_host(tp).copy()
+        s2, trKi = s * s, tr
+        trKK = tph[nth * nth - 1]
+        tph[0 * nth + 0] = ch * ch * (n - 2.0 * s2 * trKi + s2 * s2 * trKK)          # tr(P_h P_h)
+        tph[0 * nth + n_p] = ch * (trKi - s2 * trKK)                                 # tr(Ki P_h)
+        for j in dense:
+            v = ch * (t1g[j] - s2 * tph[j * nth + n_p])                              # tr(P_h P_j)
+            tph[0 * nth + j] = tph[j * nth + 0] = v
         G = np.zeros((nth, nth))
         Q = np.zeros((nth, nth))
         TP = np.zeros((nth, nth))

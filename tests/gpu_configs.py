@@ -69,8 +69,17 @@ def c1():
         gp.log_lh, gp.dloglh_dtheta, gp.mean(xo), gp.cov(xo)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
+    # the reference's own path (oracle/_ref + scipy/numpy) on the host cores, same bundle
+    oracle = load_oracle()
+    impl = "ref" if oracle.have_ref() else "c"
+    t0 = time.perf_counter()
+    for k in range(reps):
+        o = oracle.OracleGP(oracle.GAUSSIAN, (1.0, 0.2 + 1e-6 * (k + 1)), x, y, 0.0, impl)
+        o.log_lh, o.dloglh_dtheta, o.mean(xo), o.cov(xo)
+    dtc = (time.perf_counter() - t0) / reps
     emit(dict(config="C1", metric="bundles/s (log_lh+grad+mean+cov, N=50, M=100)", value=1 / dt,
-              ms_per_bundle=dt * 1e3, parity_vs_reference=errs))
+              ms_per_bundle=dt * 1e3, parity_vs_reference=errs, cpu_reference_ms_per_bundle=dtc * 1e3,
+              note="launch-latency regime: ~40 dependent launches and 6 host read-backs per bundle"))
 
 
 def c2():
