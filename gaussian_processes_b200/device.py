@@ -9,14 +9,24 @@ NB = 128          # GPB_BLOCK: padding / blocking unit of device matrices
 F64 = torch.float64
 
 
+_cuda_ok = False
+
+
 def require_cuda():
-    if not torch.cuda.is_available():
-        raise _lib.GpbError("gaussian_processes_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    """The current CUDA device (raises when there is none: no CPU fallback).  Availability is
+    probed once -- torch.cuda.is_available() costs ~4 us per call, which is real money for a
+    50-point GP whose whole evaluation is ~20 kernel launches."""
+    global _cuda_ok
+    if not _cuda_ok:
+        if not torch.cuda.is_available():
+            raise _lib.GpbError("gaussian_processes_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _cuda_ok = True
     return torch.device("cuda", torch.cuda.current_device())
 
 
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device (raw handle, ~0.3 us)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def roundup(n, m=NB):

@@ -46,6 +46,14 @@ class Engine(object):
         self.finite = bool(np.isfinite(np.asarray(x)).all() and np.isfinite(np.asarray(y)).all())
         self._c = {}
 
+    def rebind(self, kparams, s):
+        """New hyperparameters on the same observations: results are dropped, x / y stay on the
+        device (what an optimiser iteration needs; the reference rebuilds everything, gp.py:231-240)."""
+        self.kparams = [float(v) for v in kparams]
+        self.s = float(s)
+        self._c = {k: v for k, v in self._c.items() if k in ("partial", "Ki_buf")}
+        return self
+
     # ------------------------------------------------------------------ helpers
     def _theta(self):
         return darr(self.kparams)
@@ -388,10 +396,31 @@ class Engine(object):
         C = self.build(dxr, mb, dxo, m, mbp, mp, 1)[0]
         P = self._panel(mbp)
 
+        # The shard's own diagonal block C[:, lo:hi] is symmetric: when it is tile-aligned, compute its
+        # lower tiles only (mirrored), bottom-up like ``cov``, and the columns left / right of it densely.
+        sym = (lo % D.NB == 0) and (mb == mbp) and (mbp >= 2 * D.NB)
+
         def blocks():
-            for r0 in range(0, mbp, P):
-                r1 = min(mbp, r0 + P)
-                self.gemm(U[r0:r1], Kall, C[r0:r1], r1 - r0, mp, self.npad, alpha=-1.0, beta=1.0)
+            if not sym:
+                for r0 in range(0, mbp, P):
+                    r1 = min(mbp, r0 + P)
+                    self.gemm(U[r0:r1], Kall, C[r0:r1], r1 - r0, mp, self.npad, alpha=-1.0, beta=1.0)
+                    yield r0, r1
+                return
+            Kd = Kall[lo:lo + mbp]
+            for r1 in range(mbp, 0, -P):
+                r0 = max(0, r1 - P)
+                Ub = U[r0:r1]
+                if lo > 0:
+                    self.gemm(Ub, Kall[:lo], C[r0:r1, :lo], r1 - r0, lo, self.npad, alpha=-1.0, beta=1.0)
+                if lo + mbp < mp:
+                    self.gemm(Ub, Kall[lo + mbp:], C[r0:r1, lo + mbp:], r1 - r0, mp - lo - mbp, self.npad,
+                              alpha=-1.0, beta=1.0)
+                if r0 > 0:
+                    self.gemm(Ub, Kd[:r0], C[r0:r1, lo:lo + r0], r1 - r0, r0, self.npad, alpha=-1.0, beta=1.0,
+                              Ct=C[:r0, lo + r0:lo + r1])
+                Cd = C[r0:r1, lo + r0:lo + r1]
+                self.gemm(Ub, Kd[r0:r1], Cd, r1 - r0, r1 - r0, self.npad, alpha=-1.0, beta=1.0, lower_only=1, Ct=Cd)
                 yield r0, r1
         return self._rows_out(C, mb, m, blocks(), host)
 

@@ -99,9 +99,12 @@ class GP(object):
         """Deep (default) or shallow copy of the GP."""
         return _copy.deepcopy(self) if deep else _copy.copy(self)
 
-    def _reset(self):
+    def _reset(self, data=False):
+        """Every setter empties the memo (gp.py:231-240); only new observations drop the device
+        copy of x / y -- new hyperparameters rebind the resident engine."""
         self._memoized = {}
-        self._dev = None
+        if data:
+            self._dev = None
 
     # ------------------------------------------------------------------ inputs (gp.py:129-240)
     @property
@@ -112,7 +115,7 @@ class GP(object):
     @x.setter
     def x(self, val):
         if np.any(val != self._x):
-            self._reset()
+            self._reset(data=True)
             self._x = np.array(val, copy=True, dtype=DTYPE)
             self._x.flags.writeable = False
 
@@ -124,7 +127,7 @@ class GP(object):
     @y.setter
     def y(self, val):
         if np.any(val != self._y):
-            self._reset()
+            self._reset(data=True)
             self._y = np.array(val, copy=True, dtype=DTYPE)
             self._y.flags.writeable = False
             if self._y.shape != self._x.shape:
@@ -174,8 +177,10 @@ class GP(object):
         """Device-side twin of the current (K, x, y, s); dropped by every setter."""
         kp = tuple(float(v) for v in self.K.params)
         key = (type(self.K).KIND, kp, float(self._s))
-        if self._dev is None or self._dev[0] != key:
+        if self._dev is None or self._dev[0][0] != key[0]:
             self._dev = (key, _engine.Engine(key[0], kp, key[2], self._x, self._y))
+        elif self._dev[0] != key:           # same observations and kernel family, new hyperparameters
+            self._dev = (key, self._dev[1].rebind(kp, key[2]))
         return self._dev[1]
 
     def _n_theta(self):

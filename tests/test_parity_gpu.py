@@ -365,3 +365,20 @@ def test_fit_mlii_refine_reaches_scipy_optimum(oracle):
         return -float(og.log_lh), -(og.dloglh_dtheta * t)
     ref = minimize(neg, np.log(cand[res.best_index]), jac=True, method="L-BFGS-B", options=dict(gtol=1e-8, maxiter=200))
     assert res.best_log_lh >= -ref.fun - 1e-6 * abs(ref.fun)
+
+
+def test_cov_rows_aligned_shards_use_symmetry(oracle):
+    """Tile-aligned shards (what M = 16384 over 2/4/8 GPUs gives) take the symmetric diagonal-block
+    path of cov_rows; stitched together they reproduce the oracle's covariance and ``cov``."""
+    x, y = synth_xy(200, 9)
+    m = 1024
+    xo = np.linspace(-6, 6, m)
+    gp = GP(PeriodicKernel(1.0, 1.0, 1.3), x, y, s=0.8)
+    ref = oracle.OracleGP(oracle.PERIODIC, (1.0, 1.0, 1.3), x, y, 0.8).cov(xo)
+    full = gp.cov(xo)
+    assert_parity(full, ref)
+    for G in (2, 4):
+        parts = [gp.cov_rows(xo, r * m // G, (r + 1) * m // G) for r in range(G)]
+        st = np.concatenate(parts, axis=0)
+        assert_parity(st, ref, RTOL, "G=%d" % G)
+        assert np.max(np.abs(st - st.T)) <= 1e-12 * np.max(np.abs(ref))
