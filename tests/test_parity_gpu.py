@@ -382,3 +382,17 @@ def test_cov_rows_aligned_shards_use_symmetry(oracle):
         st = np.concatenate(parts, axis=0)
         assert_parity(st, ref, RTOL, "G=%d" % G)
         assert np.max(np.abs(st - st.T)) <= 1e-12 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("n1,n2", [(3, 1100000), (3000, 33), (1500, 700)])
+def test_builders_large_and_skinny_downloads(oracle, n1, n2):
+    """Host-buffer builders whose results take the different staged-download shapes: a single row
+    longer than a pinned slot (column split), many short rows (re-tiled as one contiguous run) and
+    multi-chunk slices; bit-level agreement is not required, the 1e-9 bar is."""
+    rng = np.random.RandomState(n1 + n2)
+    x1, x2 = rng.uniform(-6, 6, n1), rng.uniform(-6, 6, n2)
+    k = GaussianKernel(1.1, 0.7)
+    assert_parity(k.K(x1, x2), oracle.kernel_K(oracle.GAUSSIAN, (1.1, 0.7), x1, x2), RTOL, "K")
+    assert_parity(k.jacobian(x1, x2), oracle.kernel_jacobian(oracle.GAUSSIAN, (1.1, 0.7), x1, x2), RTOL, "jacobian")
+    out = np.full((n1, n2), np.nan)
+    assert k.dK_dw(x1, x2, out=out) is out and not np.isnan(out).any()
