@@ -28,6 +28,16 @@ namespace {
 // completely idle SM -- this is what lets the serial part of one group's factorisation overlap
 // the trailing updates of the others.  (Stream priorities for this kernel were measured: no gain.)
 //
+// Measured trade-offs behind the structure (tests/gpu_diag_clk.py, profiles/README.md):
+//   * the 32x32 sweeps (P1) and substitutions (P2/P3) are FULLY UNROLLED although that makes the
+//     kernel ~150 KB of SASS against a 32 KB L1.5 instruction cache (warp sampling: a third of the
+//     active issue slots wait on instruction fetch, and the small DMMA phases pay for it).  A fully
+//     rolled variant (shifted register slots, 24 KB of code) was built and measured: the DMMA
+//     phases got 2x faster, but the single-warp phases got slower by more (P1 8.5k -> 10.4k,
+//     P2/P3 2.9k -> 8.1k cycles per step: twice the FMAs, no triangular savings), 105k vs 78k cycles.
+//   * one warp issues dependent DFMA every 8 cycles, a 64-bit shuffle costs 26, rsqrt 66: the
+//     column sweep is bound by that chain (~265 cycles per column), not by throughput.
+//
 // Per 32-column step bb:
 //   P1  warp 0        Cholesky of the 32x32 diagonal sub-block in registers (lane = row,
 //                     pivots / columns by warp shuffle, rsqrt on the critical path)
@@ -36,6 +46,9 @@ namespace {
 //   P4  all warps     trailing update inside the tile on DMMA
 // then W = L^-1 is completed block by block (DMMA), results streamed to W / V = W^T.
 // ===========================================================================
+#ifndef DIAG_MIN_CTAS
+#define DIAG_MIN_CTAS 2
+#endif
 constexpr int SB = 32;            // sub-block edge
 constexpr int SLD = 36;           // padded stride: 36 = 4 (mod 16) -> conflict-free DMMA fragment loads
 constexpr int SBSZ = SB * SLD;
@@ -110,7 +123,7 @@ __device__ __forceinline__ void strip_to_wv(const double (&acc)[2][4][2], double
         }
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, DIAG_MIN_CTAS)
 potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ldw, long long sW,
                   double* V, long long ldv, long long sV, int* info, int col0) {
     extern __shared__ __align__(16) double sm[];
