@@ -66,6 +66,7 @@ static GpbOption g_options[] = {
     {"eval_streams", "GPB_EVAL_STREAMS", 0, false},   // candidate groups evaluated on concurrent streams
     {"gemm_bm", "GPB_GEMM_BM", 0, false},             // 64 (2 CTAs/SM) or 128 row tiles
     {"potrf_inner", "GPB_POTRF_INNER", 0, false},     // 128-columns per outer Cholesky panel
+    {"potrf_lookahead", "GPB_POTRF_LOOKAHEAD", 0, false},   // 0 = panel look-ahead for one matrix of N >= 6144, 1 = always, 2 = off
     {"gemm_impl", "GPB_GEMM_IMPL", 0, false},         // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
 };
 int gpb_get_option(const char* name) {

@@ -678,6 +678,31 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     // matrix as a plain 128-wide right-looking sweep, each with a longer DMMA main loop.
     int inner = gpb_get_option("potrf_inner");
     if (inner < 1) inner = 4;
+
+    // Look-ahead for a single matrix (a batch keeps the GPU busy by itself): the serial panel
+    // factorisation runs on a high-priority side stream `ps`, and each trailing update is split in
+    //   SYRK_a  the columns of the NEXT panel (on `ps`, the only part the next panel needs), and
+    //   SYRK_b  the rest of the trailing matrix (on `st`, overlapping the next panel's serial work;
+    //           the panel kernels' CTAs take freed SM slots first because of their stream priority).
+    static thread_local cudaStream_t la_stream = nullptr;      // one per host thread (one thread per stream, gpb200.h)
+    static thread_local cudaEvent_t la_ev[4];
+    // Measured (tests/gpu_potrf_la.py): N = 8192 / 16384 / 32768 gain 11 / 11 / 4 % (34.2 TFLOP/s at
+    // 32768); at N <= 4096 the trailing updates are too short to pay for the co-scheduling.
+    const int la_opt = gpb_get_option("potrf_lookahead");
+    const bool lookahead = (batch == 1) && (T > inner) && (la_opt != 2) && (T >= 48 || la_opt == 1);
+    if (lookahead && !la_stream) {
+        int lo = 0, hi = 0;
+        GPB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        GPB_CUDA(cudaStreamCreateWithPriority(&la_stream, cudaStreamNonBlocking, hi));
+        for (auto& e : la_ev) GPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t ps = lookahead ? la_stream : st;
+    cudaEvent_t ev_start = la_ev[0], ev_panel = la_ev[1], ev_b = la_ev[2], ev_end = la_ev[3];
+    bool have_b = false;
+    if (lookahead) {
+        GPB_CUDA(cudaEventRecord(ev_start, st));
+        GPB_CUDA(cudaStreamWaitEvent(ps, ev_start, 0));
+    }
     for (int k0 = 0; k0 < T; k0 += inner) {
         const int kw = (T - k0 < inner) ? (T - k0) : inner;
         const long long p0 = (long long)k0 * GPB_NB;
@@ -691,12 +716,12 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
                 c.C = A + o * ld + o; c.ldc = ld; c.sC = sA;
                 c.M = (T - k) * GPB_NB; c.N = GPB_NB; c.K = q * GPB_NB;
                 c.alpha = -1.0; c.beta = 1.0;
-                int stt = gpb_launch_gemm(c, batch, st);
+                int stt = gpb_launch_gemm(c, batch, ps);
                 if (stt != GPB_OK) return stt;
             }
             {
-                GpbProfScope prof(GPB_KC_DIAG, st);
-                potrf_diag_kernel<<<batch, 256, DIAG_SMEM, st>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
+                GpbProfScope prof(GPB_KC_DIAG, ps);
+                potrf_diag_kernel<<<batch, 256, DIAG_SMEM, ps>>>(A + o * ld + o, ld, sA, W + o * ldw + o, ldw, sW,
                                                                  V ? V + o * ldv + o : nullptr, ldv, sV, info,
                                                                  (int)o);
                 GPB_LAUNCH_CHECK("potrf_diag_kernel");
@@ -709,21 +734,59 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
             g.C = A + (o + GPB_NB) * ld + o; g.ldc = ld; g.sC = sA;
             g.M = rem; g.N = GPB_NB; g.K = GPB_NB;
             g.b_tri = 1;                               // W_kk lower: k <= j
-            int stt = gpb_launch_gemm(g, batch, st);
+            int stt = gpb_launch_gemm(g, batch, ps);
             if (stt != GPB_OK) return stt;
         }
         const long long t0 = (long long)(k0 + kw) * GPB_NB;
         const int rem2 = (T - k0 - kw) * GPB_NB;
-        if (rem2 > 0) {                                // trailing: A_ij -= P_i P_j^T (lower tiles)
-            GpbGemm u = gpb_gemm_default();
-            u.A = A + t0 * ld + p0; u.lda = ld; u.sA = sA;
-            u.B = A + t0 * ld + p0; u.ldb = ld; u.sB = sA;
-            u.C = A + t0 * ld + t0; u.ldc = ld; u.sC = sA;
-            u.M = rem2; u.N = rem2; u.K = kw * GPB_NB;
-            u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+        if (rem2 <= 0) continue;
+        GpbGemm u = gpb_gemm_default();                // trailing: A_ij -= P_i P_j^T (lower tiles)
+        u.A = A + t0 * ld + p0; u.lda = ld; u.sA = sA;
+        u.B = A + t0 * ld + p0; u.ldb = ld; u.sB = sA;
+        u.C = A + t0 * ld + t0; u.ldc = ld; u.sC = sA;
+        u.M = rem2; u.N = rem2; u.K = kw * GPB_NB;
+        u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+        if (!lookahead) {
             int stt = gpb_launch_gemm(u, batch, st);
             if (stt != GPB_OK) return stt;
+            continue;
         }
+        const int w = ((rem2 / GPB_NB < inner) ? rem2 / GPB_NB : inner) * GPB_NB;     // next panel's width
+        // SYRK_b (rows/cols beyond the next panel) on st, as soon as this panel's P is complete
+        if (rem2 > w) {
+            GPB_CUDA(cudaEventRecord(ev_panel, ps));
+            GPB_CUDA(cudaStreamWaitEvent(st, ev_panel, 0));
+            GpbGemm ub = u;
+            ub.A = u.A + (long long)w * ld; ub.B = ub.A;
+            ub.C = u.C + (long long)w * ld + w;
+            ub.M = ub.N = rem2 - w;
+            int stt = gpb_launch_gemm(ub, batch, st);
+            if (stt != GPB_OK) return stt;
+        }
+        // SYRK_a on the panel stream; it overwrites columns the previous SYRK_b also wrote
+        if (have_b) GPB_CUDA(cudaStreamWaitEvent(ps, ev_b, 0));
+        {
+            GpbGemm ua = u;                             // top w x w square, lower tiles
+            ua.M = ua.N = w;
+            int stt = gpb_launch_gemm(ua, batch, ps);
+            if (stt != GPB_OK) return stt;
+            if (rem2 > w) {                             // rows below it, all w columns
+                GpbGemm ur = u;
+                ur.A = u.A + (long long)w * ld;
+                ur.C = u.C + (long long)w * ld;
+                ur.M = rem2 - w; ur.N = w; ur.lower_only = 0;
+                stt = gpb_launch_gemm(ur, batch, ps);
+                if (stt != GPB_OK) return stt;
+            }
+        }
+        if (rem2 > w) {
+            GPB_CUDA(cudaEventRecord(ev_b, st));
+            have_b = true;
+        }
+    }
+    if (lookahead) {
+        GPB_CUDA(cudaEventRecord(ev_end, ps));
+        GPB_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
     }
     return GPB_OK;
 }

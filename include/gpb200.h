@@ -201,7 +201,9 @@ int64_t gpb_launch_count(void);
 /* Tuning knobs (0 = built-in default; also readable from the environment):
  *   "eval_streams" (GPB_EVAL_STREAMS) candidate groups evaluated on concurrent streams by gpb_gp_eval
  *   "gemm_bm"      (GPB_GEMM_BM)      64 (two CTAs per SM) or 128 row tiles in the DMMA GEMM
- *   "potrf_inner"  (GPB_POTRF_INNER)  128-columns per outer Cholesky panel                    */
+ *   "potrf_inner"  (GPB_POTRF_INNER)  128-columns per outer Cholesky panel
+ *   "potrf_lookahead" (GPB_POTRF_LOOKAHEAD) panel look-ahead of a single factorisation: 0 auto (N >= 6144), 1 on, 2 off
+ *   "gemm_impl"    (GPB_GEMM_IMPL)    0 TMA + mbarrier operand pipeline, 1 cp.async pipeline                */
 int gpb_set_option(const char* name, int value);
 /* Per-kernel-class device timing: while enabled, each launch group of a class is bracketed
  * by CUDA events on its stream.  Classes: 0 DMMA GEMM, 1 diagonal-block factor, 2 kernel
