@@ -221,6 +221,15 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
+// Two variants of this kernel were built and measured and are deliberately NOT used:
+//   * 112 registers per thread (no spill headroom needed): a sub-partition holds 16384 registers and the
+//     2 x 9 warps of two co-resident CTAs put up to 5 warps on one of them, so anything above 96
+//     registers silently drops the SM to one resident CTA (458 -> 402 evals/s);
+//   * a persistent grid (2 CTAs per SM walking the tile list, stage ring running on across tiles):
+//     removes the per-tile pipeline fill, but the resident CTAs then hold every SM slot for the whole
+//     launch, so the serial kernels of the other candidate groups (and the look-ahead panel stream)
+//     can no longer slip in between tiles, and static tile assignment loses the hardware's dynamic
+//     balance: 458 -> 435 evals/s, N=16384 potrf 52.7 -> 57.7 ms.
 template <int BM> struct TmaCfg {
     static constexpr int CONSUMERS = BM * 4;               // threads: (BM/32) x 4 warps of 32 x 32
     static constexpr int THREADS = CONSUMERS + 32;         // + one producer warp
