@@ -63,6 +63,11 @@ _PROTOS = {
     "gpb_eval_workspace_bytes": (c_size_t, [_i64, c_int, c_int]),
     "gpb_gp_eval": (c_int, [c_int, dp, c_int, vp, vp, _i64, c_int, vp, c_size_t, vp, vp]),
     "gpb_gp_eval_host": (c_int, [c_int, dp, c_int, dp, dp, _i64, c_int, dp]),
+    "gpb_eval_layout": (c_int, [_i64, POINTER(c_int64), c_int]),
+    "gpb_gp_stages": (c_int, [c_int, dp, vp, vp, _i64, c_uint, vp, c_size_t, vp, vp]),
+    "gpb_post_mean_host": (c_int, [c_int, dp, vp, _i64, vp, _i64, vp, vp, vp, vp]),
+    "gpb_post_cov_scratch_doubles": (c_size_t, [_i64, _i64]),
+    "gpb_post_cov_host": (c_int, [c_int, dp, vp, _i64, vp, _i64, vp, _i64, vp, vp, _i64, vp]),
     "gpb_kernel_slices_host": (c_int, [c_int, c_uint, vp, vp, _i64, vp, _i64, dp]),
     "gpb_microbench_fp64": (c_int, [c_int, c_int, dp, dp]),
     "gpb_microbench_latency": (c_int, [dp]),

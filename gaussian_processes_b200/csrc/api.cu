@@ -160,8 +160,9 @@ __global__ void eval_finalize_kernel(const double* out3, const double* out8, con
     r[7] = (double)info[b];
 }
 
+#define GPB_STAGE_PACK 24      // doubles read back by gpb_gp_stages: out3 | out16 | info | pad
 struct EvalWs {
-    double *L, *W, *V, *Ki, *z, *alpha, *ypad, *partial, *out3, *out8;
+    double *L, *W, *V, *Ki, *z, *alpha, *ypad, *partial, *out3, *out8, *pack;
     KParams* Pb;
     int *info, *flags;
     size_t bytes;
@@ -187,6 +188,7 @@ static EvalWs carve(char* base, long long n, int batch, int want_grad) {
     w.Pb = (KParams*)take((size_t)batch * sizeof(KParams));
     w.info = (int*)take((size_t)batch * 4);
     w.flags = (int*)take(((size_t)2 * batch * T + 2) * 4);
+    w.pack = (double*)take(GPB_STAGE_PACK * 8);
     w.bytes = off;
     return w;
 }
@@ -513,21 +515,29 @@ static int eval_group(int kind, const double* thetas, int batch, const double* x
     // the factorisation reads the lower triangle only: skip the tiles above it (half the exp work)
     stt = gpb_launch_build(kind, nullptr, w.Pb, batch, x, n, x, n, np_, np_, outs, np_, mstride, 1, 1, st, 1);
     if (stt) return stt;
-    stt = gpb_launch_potrf(w.L, np_, np_, mstride, batch, w.W, np_, mstride, want_grad ? w.V : nullptr, np_, mstride, w.info, st);
+    stt = gpb_launch_potrf(w.L, np_, np_, mstride, batch, w.W, np_, mstride, want_grad ? w.V : nullptr, np_, mstride, w.info, st, n);
     if (stt) return stt;
-    stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, mstride, mstride, batch, w.ypad, 0, w.z, w.alpha, np_, w.flags, st);
-    if (stt) return stt;
-    stt = gpb_launch_loglh(w.L, n, np_, mstride, batch, w.ypad, 0, w.alpha, np_, w.info, w.out3, st);
-    if (stt) return stt;
-    if (want_grad) {
-        stt = gpb_launch_trtri(w.L, np_, np_, mstride, batch, w.W, np_, mstride, w.V, np_, mstride, w.Ki, np_, mstride, st);
+    if (np_ == GPB_NB) {
+        // one 128-block per candidate: solves, log_lh, K^-1 and the gradient brackets in ONE launch
+        stt = gpb_launch_small_tail(kind, nullptr, w.Pb, batch, x, n, w.ypad, 0, w.L, np_, mstride, w.W, np_, mstride,
+                                    want_grad ? w.Ki : nullptr, np_, mstride, w.z, w.alpha, np_, w.info, w.out3,
+                                    w.out8, st);
         if (stt) return stt;
-        stt = gpb_launch_lauum(w.V, np_, np_, mstride, batch, w.Ki, np_, mstride, st);
+    } else {
+        stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, mstride, mstride, batch, w.ypad, 0, w.z, w.alpha, np_, w.flags, st);
         if (stt) return stt;
-        const int jsl[3] = {1, 2, 3};
-        stt = gpb_launch_grad_reduce(kind, nullptr, w.Pb, batch, x, n, w.Ki, np_, mstride, w.alpha, np_,
-                                     gpb_n_kparams(kind), jsl, w.partial, w.out8, st);
+        stt = gpb_launch_loglh(w.L, n, np_, mstride, batch, w.ypad, 0, w.alpha, np_, w.info, w.out3, st);
         if (stt) return stt;
+        if (want_grad) {
+            stt = gpb_launch_trtri(w.L, np_, np_, mstride, batch, w.W, np_, mstride, w.V, np_, mstride, w.Ki, np_, mstride, st);
+            if (stt) return stt;
+            stt = gpb_launch_lauum(w.V, np_, np_, mstride, batch, w.Ki, np_, mstride, st);
+            if (stt) return stt;
+            const int jsl[3] = {1, 2, 3};
+            stt = gpb_launch_grad_reduce(kind, nullptr, w.Pb, batch, x, n, w.Ki, np_, mstride, w.alpha, np_,
+                                         gpb_n_kparams(kind), jsl, w.partial, w.out8, st);
+            if (stt) return stt;
+        }
     }
     eval_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.out3, w.out8, w.info, w.Pb, kind, want_grad, batch, result);
     GPB_LAUNCH_CHECK("eval_finalize_kernel");
@@ -581,6 +591,174 @@ int gpb_gp_eval_host(int kind, const double* thetas, int batch, const double* x,
     if (stt) return stt;
     GPB_CUDA(cudaMemcpyAsync(result, dres, (size_t)batch * 8 * 8, cudaMemcpyDeviceToHost, 0));
     GPB_CUDA(cudaStreamSynchronize(0));
+    return GPB_OK;
+}
+
+// ---- one GP, caller-resident buffers, staged: what GP.log_lh / dloglh_dtheta / cov need ----
+// The property chain of a single GP object used to be ~12 library calls and 3 blocking read-backs
+// from Python; at the reference's own test-suite scale (N = 50) that host latency IS the cost.
+// Here the whole chain is enqueued by one call and everything the host needs comes back in one
+// 192-byte transfer.
+__global__ void stage_pack_kernel(const double* out3, const double* out16, const int* info, double* pack) {
+    const int t = threadIdx.x;
+    if (t < 3) pack[t] = out3[t];
+    else if (t < 19) pack[t] = out16[t - 3];
+    else if (t == 19) pack[t] = (double)info[0];
+    else if (t < GPB_STAGE_PACK) pack[t] = 0.0;
+}
+
+int gpb_eval_layout(int64_t n, int64_t* off, int noff) {
+    GPB_REQUIRE(n >= 1 && off && noff >= 15, "bad argument");
+    char* base = reinterpret_cast<char*>((uintptr_t)1 << 20);
+    EvalWs w = carve(base, n, 1, 1);
+    const void* p[14] = {w.L, w.W, w.V, w.Ki, w.z, w.alpha, w.ypad, w.partial, w.out3, w.out8, w.Pb, w.info, w.flags, w.pack};
+    for (int i = 0; i < 14; i++) off[i] = (int64_t)((const char*)p[i] - base);
+    off[14] = (int64_t)w.bytes;
+    return GPB_OK;
+}
+
+int gpb_gp_stages(int kind, const double* theta, const double* x, const double* ypad, int64_t n,
+                  unsigned stages, void* workspace, size_t workspace_bytes, double* host_out, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(n >= 1 && theta && x && ypad && workspace, "bad argument");
+    GPB_REQUIRE((uintptr_t)workspace % 256 == 0, "workspace must be 256-byte aligned");
+    EvalWs w = carve((char*)workspace, n, 1, 1);
+    GPB_REQUIRE(w.bytes <= workspace_bytes, "workspace too small (see gpb_eval_layout)");
+    cudaStream_t st = S(stream);
+    const long long np_ = roundup(n, GPB_NB);
+    const int nkp = gpb_n_kparams(kind);
+    KParams P;
+    gpb_make_kparams(&P, kind, theta, theta[nkp]);
+    int stt;
+    unsigned done = 0;
+    if (np_ == GPB_NB) {
+        // a GP that fits one 128-block: build, factor + invert (one CTA), then everything else in
+        // one more launch -- all four stages at once, whatever subset was asked for
+        if (stages & 1u) {
+            double* outs[GPB_MAX_SLICES] = {nullptr};
+            outs[0] = w.L;
+            stt = gpb_launch_build(kind, &P, nullptr, 1, x, n, x, n, np_, np_, outs, np_, 0, 1, 1, st, 1);
+            if (stt) return stt;
+            stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n);
+            if (stt) return stt;
+            stt = gpb_launch_small_tail(kind, &P, nullptr, 1, x, n, ypad, 0, w.L, np_, 0, w.W, np_, 0, w.Ki, np_, 0,
+                                        w.z, w.alpha, np_, w.info, w.out3, w.out8, st);
+            if (stt) return stt;
+            done = 15u;
+        }
+        stages = 0;
+    }
+    if (stages & 1u) {          // Kxx + s^2 I (lower tiles) -> L, W_kk, V_kk, info; alpha; log_lh
+        double* outs[GPB_MAX_SLICES] = {nullptr};
+        outs[0] = w.L;
+        stt = gpb_launch_build(kind, &P, nullptr, 1, x, n, x, n, np_, np_, outs, np_, 0, 1, 1, st, 1);
+        if (stt) return stt;
+        stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n);
+        if (stt) return stt;
+        stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, 0, 0, 1, ypad, 0, w.z, w.alpha, np_, w.flags, st);
+        if (stt) return stt;
+        stt = gpb_launch_loglh(w.L, n, np_, 0, 1, ypad, 0, w.alpha, np_, w.info, w.out3, st);
+        if (stt) return stt;
+    }
+    if (stages & 2u) {          // W = L^-1, V = L^-T
+        stt = gpb_launch_trtri(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.Ki, np_, 0, st);
+        if (stt) return stt;
+    }
+    if (stages & 4u) {          // Ki = V V^T
+        stt = gpb_launch_lauum(w.V, np_, np_, 0, 1, w.Ki, np_, 0, st);
+        if (stt) return stt;
+    }
+    if (stages & 8u) {          // a^T dK_i a, sum(Ki o dK_i), tr Ki, a.a
+        const int jsl[3] = {1, 2, 3};
+        stt = gpb_launch_grad_reduce(kind, &P, nullptr, 1, x, n, w.Ki, np_, 0, w.alpha, np_, nkp, jsl, w.partial,
+                                     w.out8, st);
+        if (stt) return stt;
+    }
+    done |= stages & 15u;
+    if (host_out) {
+        stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, w.out8, w.info, w.pack);
+        GPB_LAUNCH_CHECK("stage_pack_kernel");
+        int slot;
+        void* hp;
+        stt = pin_acquire(GPB_STAGE_PACK * 8, &slot, &hp);
+        if (stt) return stt;
+        GPB_CUDA(cudaMemcpyAsync(hp, w.pack, GPB_STAGE_PACK * 8, cudaMemcpyDeviceToHost, st));
+        GPB_CUDA(cudaStreamSynchronize(st));
+        memcpy(host_out, hp, GPB_STAGE_PACK * 8);
+        host_out[20] = (double)done;       // stages this call completed (a one-block GP completes all four)
+    }
+    return GPB_OK;
+}
+
+// posterior mean with host buffers in and out: K(xo, x) alpha, the M x N kernel matrix never
+// materialised (gp.py:574-597).  scratch: DEVICE, >= 2 * roundup(m, 32) doubles.
+int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int64_t m, const double* x,
+                       int64_t n, const double* alpha, double* scratch, double* out_host, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(m >= 0 && n >= 1 && theta && x && alpha, "bad argument");
+    if (m == 0) return GPB_OK;
+    GPB_REQUIRE(xo_host && scratch && out_host, "null pointer");
+    cudaStream_t st = S(stream);
+    const long long mr = roundup(m, 32);
+    KParams P;
+    gpb_make_kparams(&P, kind, theta, 0.0);
+    GPB_CUDA(cudaMemcpyAsync(scratch, xo_host, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    const int sl[1] = {0}, oi[1] = {0};
+    const double cf[1] = {1.0};
+    const double* vec[1] = {alpha};
+    double* out[1] = {scratch + mr};
+    int stt = gpb_launch_fused_matvec(kind, &P, nullptr, 1, scratch, m, x, n, 1, sl, oi, cf, vec, 1, out, 0, 0, st);
+    if (stt) return stt;
+    GPB_CUDA(cudaMemcpyAsync(out_host, scratch + mr, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    GPB_CUDA(cudaStreamSynchronize(st));
+    return GPB_OK;
+}
+
+// posterior covariance with host buffers in and out, for test sets whose M x M result is small
+// enough that pipelining its download does not pay (gp.py:599-625):
+//   cov = K(xo,xo) - Z Z^T,  Z = K(xo,x) L^-T  (W = L^-1 from gpb_trtri / gpb_gp_stages).
+// scratch: DEVICE, >= gpb_post_cov_scratch_doubles(m, n) doubles, 256-byte aligned.
+size_t gpb_post_cov_scratch_doubles(int64_t m, int64_t n) {
+    const size_t mp = (size_t)roundup(m, GPB_NB), np_ = (size_t)roundup(n, GPB_NB);
+    return mp + 2 * mp * np_ + mp * mp;
+}
+int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int64_t m, const double* x,
+                      int64_t n, const double* W, int64_t ldw, double* scratch, double* out_host,
+                      int64_t ld_out, void* stream) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(m >= 0 && n >= 1 && theta && x && W, "bad argument");
+    if (m == 0) return GPB_OK;
+    GPB_REQUIRE(xo_host && scratch && out_host && ld_out >= m, "bad argument");
+    GPB_REQUIRE((uintptr_t)scratch % 256 == 0, "scratch must be 256-byte aligned");
+    cudaStream_t st = S(stream);
+    const long long mp = roundup(m, GPB_NB), np_ = roundup(n, GPB_NB);
+    double* dxo = scratch;
+    double* Kxox = dxo + mp;
+    double* Z = Kxox + mp * np_;
+    double* C = Z + mp * np_;
+    KParams P;
+    gpb_make_kparams(&P, kind, theta, 0.0);
+    GPB_CUDA(cudaMemcpyAsync(dxo, xo_host, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    double* outs[GPB_MAX_SLICES] = {nullptr};
+    outs[0] = Kxox;
+    int stt = gpb_launch_build(kind, &P, nullptr, 1, dxo, m, x, n, mp, np_, outs, np_, 0, 0, 0, st);
+    if (stt) return stt;
+    GpbGemm g = gpb_gemm_default();                 // Z = Kxox W^T   (W lower)
+    g.A = Kxox; g.lda = np_; g.B = W; g.ldb = ldw; g.C = Z; g.ldc = np_;
+    g.M = (int)mp; g.N = (int)np_; g.K = (int)np_; g.b_tri = 1;
+    stt = gpb_launch_gemm(g, 1, st);
+    if (stt) return stt;
+    outs[0] = C;
+    stt = gpb_launch_build(kind, &P, nullptr, 1, dxo, m, dxo, m, mp, mp, outs, mp, 0, 0, 0, st);
+    if (stt) return stt;
+    GpbGemm u = gpb_gemm_default();                 // C -= Z Z^T (lower tiles, mirrored)
+    u.A = Z; u.lda = np_; u.B = Z; u.ldb = np_; u.C = C; u.ldc = mp; u.Ct = C; u.ldct = mp;
+    u.M = (int)mp; u.N = (int)mp; u.K = (int)np_; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+    stt = gpb_launch_gemm(u, 1, st);
+    if (stt) return stt;
+    stt = d2h_staged(out_host, ld_out, C, mp, m, m, st);
+    if (stt) return stt;
+    GPB_CUDA(cudaStreamSynchronize(st));
     return GPB_OK;
 }
 

@@ -61,7 +61,7 @@ int gpb_launch_post_var(int kind, const KParams* P, const double* Z, long long l
 // potrf.cu
 int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
-                     cudaStream_t st);
+                     cudaStream_t st, long long n_valid = 0);   // n_valid: rows that are not identity pad (0 = n)
 int gpb_launch_trtri(const double* L, long long n, long long ld, long long sL, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, double* T,
                      long long ldt, long long sT, cudaStream_t st);
@@ -76,6 +76,13 @@ int gpb_launch_loglh(const double* L, long long n_valid, long long ld, long long
 int gpb_launch_tril(double* A, long long n, long long ld, long long sA, int batch, cudaStream_t st);
 int gpb_launch_copy2d(double* dst, long long ldd, const double* src, long long lds, long long rows,
                       long long cols, long long sD, long long sS, int batch, cudaStream_t st);
+
+// small.cu: everything after the factorisation of a one-block GP (n <= 128) in one launch
+int gpb_launch_small_tail(int kind, const KParams* P, const KParams* Pb, int batch, const double* x, long long n,
+                          const double* y, long long sy, const double* L, long long ldl, long long sL,
+                          const double* W, long long ldw, long long sW, double* Ki, long long ldk, long long sK,
+                          double* z, double* alpha, long long svec, const int* info, double* out3,
+                          double* out16, cudaStream_t st);
 
 // reduce.cu
 int gpb_launch_gemv(const double* A, long long rows, long long cols, long long lda, const double* x,

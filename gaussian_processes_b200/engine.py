@@ -33,6 +33,9 @@ def hess_slice(kind, i, j):
 class Engine(object):
     """One (kernel, theta, s, x, y) on the device; results are cached until dropped."""
 
+    # stages of gpb_gp_stages (include/gpb200.h)
+    ST_FACTOR, ST_TRTRI, ST_LAUUM, ST_GRAD = 1, 2, 4, 8
+
     def __init__(self, kind, kparams, s, x, y):
         self.kind = int(kind)
         self.n_p = N_KP[self.kind]
@@ -45,14 +48,80 @@ class Engine(object):
         self.dy = D.to_device(y, pad_to=self.npad)
         self.finite = bool(np.isfinite(np.asarray(x)).all() and np.isfinite(np.asarray(y)).all())
         self._c = {}
+        self._ws = None
+        self._done = 0
 
     def rebind(self, kparams, s):
-        """New hyperparameters on the same observations: results are dropped, x / y stay on the
-        device (what an optimiser iteration needs; the reference rebuilds everything, gp.py:231-240)."""
+        """New hyperparameters on the same observations: results are dropped, x / y and the
+        workspace stay on the device (what an optimiser iteration needs; the reference rebuilds
+        everything, gp.py:231-240)."""
         self.kparams = [float(v) for v in kparams]
         self.s = float(s)
-        self._c = {k: v for k, v in self._c.items() if k in ("partial", "Ki_buf")}
+        self._c = {k: v for k, v in self._c.items() if k in ("partial",)}
+        self._done = 0
         return self
+
+    def reset(self):
+        """Forget every result (the workspace stays allocated)."""
+        self._c = {}
+        self._done = 0
+
+    # ------------------------------------------------------------------ staged chain
+    def _workspace(self):
+        """The batch-1 evaluator workspace; L / W / V / Ki / alpha are views into it."""
+        if self._ws is None:
+            off = (ctypes.c_int64 * 16)()
+            call("gpb_eval_layout", self.n, off, 16)
+            ws = torch.empty(int(off[14]), dtype=torch.uint8, device=D.require_cuda())
+            nn = self.npad * self.npad * 8
+
+            def mat(i):
+                return ws[int(off[i]):int(off[i]) + nn].view(D.F64).view(self.npad, self.npad)
+            self._ws = ws
+            self._ws_ptr, self._ws_bytes = ws.data_ptr(), ws.numel()
+            self._mL, self._mW, self._mV, self._mKi = mat(0), mat(1), mat(2), mat(3)
+            self._valpha = ws[int(off[5]):int(off[5]) + self.npad * 8].view(D.F64)
+            self._hout = np.empty(24)
+            self._hout_ptr = self._hout.ctypes.data
+        return self._ws
+
+    def _run(self, stages):
+        """Enqueue the missing stages of the chain in ONE library call with ONE read-back."""
+        stages |= self.ST_FACTOR
+        if stages & self.ST_GRAD:
+            stages |= self.ST_LAUUM
+        if stages & self.ST_LAUUM:
+            stages |= self.ST_TRTRI
+        need = stages & ~self._done
+        if not need:
+            return
+        self._workspace()
+        call("gpb_gp_stages", self.kind, darr(self.kparams + [self.s]), D.ptr(self.dx), D.ptr(self.dy),
+             self.n, need, self._ws_ptr, self._ws_bytes, self._hout_ptr, D.stream_ptr())
+        h = self._hout
+        c = self._c
+        need |= int(h[20])          # a one-block GP (N <= 128) completes every stage in its two launches
+        if need & self.ST_FACTOR:
+            c.update(L=self._mL, W=self._mW, V=self._mV, alpha=self._valpha, info=int(h[19]),
+                     loglh3=(float(h[0]), float(h[1]), float(h[2])))
+        if need & self.ST_TRTRI:
+            c["trtri"] = True
+        if need & self.ST_LAUUM:
+            c["Ki"] = self._mKi
+        if need & self.ST_GRAD:
+            c["grad_raw"] = h[3:19].copy()
+        self._done |= need
+
+    def _ensure(self, stages):
+        """Run the chain up to ``stages`` and raise what the reference raises: ValueError for
+        non-finite data (scipy check_finite, gp.py:294), LinAlgError when Kxx is not PD."""
+        if not self.finite:
+            raise ValueError("array must not contain infs or NaNs")
+        self._run(stages)
+        info = self._c["info"]
+        if info != 0:
+            raise np.linalg.LinAlgError(
+                "%d-th leading minor of the array is not positive definite" % info)
 
     # ------------------------------------------------------------------ helpers
     def _theta(self):
@@ -100,27 +169,13 @@ class Engine(object):
         return self._c["K"]
 
     def factor(self):
-        """Blocked Cholesky (gp.py:294).  Returns LAPACK-style info (0 = ok)."""
-        if "info" not in self._c:
-            n = self.npad
-            if "K" in self._c:
-                L = self._c["K"].clone()
-            else:   # build straight into the factorisation buffer: no extra pass over HBM
-                L = self.build(self.dx, self.n, self.dx, self.n, n, n, 1, add_diag=True, pad_identity=True)[0]
-            W, V = D.empty(n, n), D.empty(n, n)
-            info = D.izeros(1)
-            call("gpb_potrf", D.ptr(L), n, n, 0, 1, D.ptr(W), n, 0, D.ptr(V), n, 0, D.ptr(info), D.stream_ptr())
-            self._c.update(L=L, W=W, V=V, info=int(info.item()))
+        """Blocked Cholesky (gp.py:294) + solves + log_lh in one enqueue.  Returns LAPACK-style
+        info (0 = ok)."""
+        self._run(self.ST_FACTOR)
         return self._c["info"]
 
     def require_pd(self):
-        if not self.finite:
-            # scipy.linalg.cholesky(check_finite=True) at gp.py:294
-            raise ValueError("array must not contain infs or NaNs")
-        info = self.factor()
-        if info != 0:
-            raise np.linalg.LinAlgError(
-                "%d-th leading minor of the array is not positive definite" % info)
+        self._ensure(self.ST_FACTOR)
 
     def Lxx_host(self):
         self.require_pd()
@@ -131,48 +186,34 @@ class Engine(object):
     def alpha(self):
         """K^-1 y by forward/backward substitution (cho_solve, gp.py:332-334); [npad], pad = 0."""
         self.require_pd()
-        if "alpha" not in self._c:
-            n = self.npad
-            z, a = D.empty(n), D.empty(n)
-            flags = D.izeros(2 * self.T + 2)
-            call("gpb_potrs", D.ptr(self._c["L"]), D.ptr(self._c["W"]), n, n, n, 0, 0, 1, D.ptr(self.dy), 0,
-                 D.ptr(z), D.ptr(a), n, D.ptr(flags), D.stream_ptr())
-            self._c["alpha"] = a
         return self._c["alpha"]
+
+    def solve(self, rhs):
+        """K^-1 rhs for another right-hand side on the cached factor (cho_solve, gp.py:332-334);
+        device vector [npad]."""
+        self.require_pd()
+        n = self.npad
+        b = D.to_device(rhs, pad_to=n)
+        z, a = D.empty(n), D.empty(n)
+        flags = D.izeros(2 * self.T + 2)
+        call("gpb_potrs", D.ptr(self._c["L"]), D.ptr(self._c["W"]), n, n, n, 0, 0, 1, D.ptr(b), 0,
+             D.ptr(z), D.ptr(a), n, D.ptr(flags), D.stream_ptr())
+        return a
 
     def inv_factor(self):
         """W = L^-1 (lower) and V = L^-T (upper), completed from potrf's diagonal blocks."""
-        self.require_pd()
-        if "trtri" not in self._c:
-            n = self.npad
-            T = self._c.get("Ki_buf")
-            if T is None:
-                T = self._c["Ki_buf"] = D.empty(n, n)
-            call("gpb_trtri", D.ptr(self._c["L"]), n, n, 0, 1, D.ptr(self._c["W"]), n, 0,
-                 D.ptr(self._c["V"]), n, 0, D.ptr(T), n, 0, D.stream_ptr())
-            self._c["trtri"] = True
+        self._ensure(self.ST_FACTOR | self.ST_TRTRI)
         return self._c["W"], self._c["V"]
 
     def Ki(self):
         """inv(L)^T inv(L) (gp.py:311-312), full symmetric [npad, npad]."""
-        if "Ki" not in self._c:
-            _, V = self.inv_factor()
-            n = self.npad
-            Ki = self._c["Ki_buf"]
-            call("gpb_lauum", D.ptr(V), n, n, 0, 1, D.ptr(Ki), n, 0, D.stream_ptr())
-            self._c["Ki"] = Ki
+        self._ensure(self.ST_FACTOR | self.ST_TRTRI | self.ST_LAUUM)
         return self._c["Ki"]
 
     # ------------------------------------------------------------------ likelihood
     def loglh3(self):
         """(log_lh, logdet, y.alpha) -- gp_c.log_lh (gp_c.pyx:17-31) with logdet from the Cholesky."""
-        if "loglh3" not in self._c:
-            a = self.alpha()
-            out = D.empty(3)
-            info = D.izeros(1)
-            call("gpb_loglh", D.ptr(self._c["L"]), self.n, self.npad, D.ptr(self.dy), D.ptr(a), D.ptr(info),
-                 D.ptr(out), D.stream_ptr())
-            self._c["loglh3"] = tuple(float(v) for v in D.to_host(out))
+        self.require_pd()
         return self._c["loglh3"]
 
     def slice_reduce(self, slices):
@@ -192,11 +233,14 @@ class Engine(object):
         return np.array(t0), np.array(t1), tr, aa
 
     def grad_terms(self):
-        """t0[i] = y^T Ki dK_i Ki y, t1[i] = tr(Ki dK_i) for the kernel params and s (gp_c.pyx:41-49)."""
+        """t0[i] = y^T Ki dK_i Ki y, t1[i] = tr(Ki dK_i) for the kernel params and s (gp_c.pyx:41-49).
+        Cold, this is the whole chain (factor, solves, inverse, fused reductions) in one call."""
         if "grad_terms" not in self._c:
-            t0, t1, tr, aa = self.slice_reduce(jac_slices(self.kind))
-            t0 = np.append(t0, 2.0 * self.s * aa)        # dK_s = 2 s I  (gp_c.pyx:45)
-            t1 = np.append(t1, 2.0 * self.s * tr)
+            self._ensure(self.ST_FACTOR | self.ST_TRTRI | self.ST_LAUUM | self.ST_GRAD)
+            h = self._c["grad_raw"]
+            n_p = self.n_p
+            t0 = np.append(h[:n_p], 2.0 * self.s * h[13])        # dK_s = 2 s I  (gp_c.pyx:45)
+            t1 = np.append(h[6:6 + n_p], 2.0 * self.s * h[12])
             self._c["grad_terms"] = (t0, t1)
         return self._c["grad_terms"]
 
@@ -286,15 +330,17 @@ class Engine(object):
 
     # ------------------------------------------------------------------ posterior
     def mean(self, xo):
-        """K(xo, x) alpha without materialising K(xo, x) (gp.py:597)."""
+        """K(xo, x) alpha without materialising K(xo, x) (gp.py:597): upload, one fused launch and
+        the download in a single library call."""
         a = self.alpha()
+        xo = np.ascontiguousarray(xo, dtype=DTYPE).reshape(-1)
         m = int(xo.size)
-        dxo = D.to_device(xo)
-        out = D.empty(max(m, 1))
+        out = np.empty(m, dtype=DTYPE)
         if m:
-            call("gpb_kernel_matvec", self.kind, self._theta(), D.ptr(dxo), m, D.ptr(self.dx), self.n, 1,
-                 iarr([0]), iarr([0]), darr([1.0]), parr([D.ptr(a)]), 1, parr([D.ptr(out)]), D.stream_ptr())
-        return D.to_host(out[:m]).copy()
+            scratch = D.empty(2 * D.roundup(m, 32))
+            call("gpb_post_mean_host", self.kind, self._theta(), xo.ctypes.data, m, D.ptr(self.dx), self.n,
+                 D.ptr(a), D.ptr(scratch), out.ctypes.data, D.stream_ptr())
+        return out
 
     def _rows_out(self, C, rows, cols, blocks, host=True):
         """Download row blocks of the device matrix ``C`` as they are produced.  ``blocks`` yields
@@ -320,6 +366,8 @@ class Engine(object):
             torch.cuda.current_stream().wait_stream(cs)      # C may be freed / reused after this
         return out
 
+    COV_HOST_MAX_M = 512      # up to here cov() is one gpb_post_cov_host call (result <= 2 MB)
+
     @staticmethod
     def _panel(mp):
         """Row-panel height for pipelined result downloads: ~8 panels, multiples of 128, >= 1024."""
@@ -335,6 +383,14 @@ class Engine(object):
         if m == 0:
             return np.empty((0, 0), dtype=DTYPE)
         mp = D.roundup(m)
+        if host and m <= self.COV_HOST_MAX_M:
+            # small result: the four launches and both copies in one library call
+            xo = np.ascontiguousarray(xo, dtype=DTYPE).reshape(-1)
+            out = np.empty((m, m), dtype=DTYPE)
+            scratch = D.empty(int(_lib.lib.gpb_post_cov_scratch_doubles(m, self.n)))
+            call("gpb_post_cov_host", self.kind, self._theta(), xo.ctypes.data, m, D.ptr(self.dx), self.n,
+                 D.ptr(W), self.npad, D.ptr(scratch), out.ctypes.data, m, D.stream_ptr())
+            return out
         dxo = D.to_device(xo)
         Kxox = self.build(dxo, m, self.dx, self.n, mp, self.npad, 1)[0]
         Z = D.empty(mp, self.npad)

@@ -156,6 +156,38 @@ int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, cons
 int gpb_gp_eval_host(int kind, const double* thetas, int batch, const double* x, const double* y,
                      int64_t n, int want_grad, double* result);
 
+/* ---- one GP object, resident buffers, staged: the property chain of gp/gp.py:242-433 for
+ * ONE theta, enqueued by one call.  The workspace is the batch-1 evaluator workspace; its
+ * layout (byte offsets of L, W, V, Ki, z, alpha, ypad, partial, out3, out16, params, info,
+ * flags, pack, then the total size; noff >= 15) comes from gpb_eval_layout so the caller can
+ * keep using L / W / V / Ki / alpha afterwards (posterior, second derivatives).
+ * stages (bit mask, run in this order):
+ *   1  Kxx + s^2 I -> Cholesky (gp.py:265,294), alpha (gp.py:332-334), log_lh (gp_c.pyx:17-31)
+ *   2  W = L^-1, V = L^-T                      4  Ki = V V^T (gp.py:311-312)
+ *   8  gradient brackets (gp_c.pyx:41-49): out16 as in gpb_slice_reduce for the Jacobian slices
+ * A GP of n <= 128 (one block) completes all four stages whenever stage 1 is asked for.
+ * theta: HOST [n_theta] (kernel params..., s).  x: DEVICE [n].  ypad: DEVICE [roundup(n,128)],
+ * zero beyond n.  host_out: HOST [24] or NULL = {log_lh, logdet, y.alpha | out16[16] | info |
+ * mask of the stages this call completed | pad};
+ * when given, the call synchronises the stream (the ONE blocking read-back of the chain).     */
+int gpb_eval_layout(int64_t n, int64_t* off, int noff);
+int gpb_gp_stages(int kind, const double* theta, const double* x, const double* ypad, int64_t n,
+                  unsigned stages, void* workspace, size_t workspace_bytes, double* host_out,
+                  void* stream);
+/* Posterior mean K(xo, x) alpha (gp.py:574-597) with HOST xo / out: upload, fused
+ * kernel-times-vector (K(xo, x) is never materialised), download, synchronise.
+ * scratch: DEVICE, >= 2 * roundup(m, 32) doubles.                                           */
+int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int64_t m,
+                       const double* x, int64_t n, const double* alpha, double* scratch,
+                       double* out_host, void* stream);
+/* Posterior covariance (gp.py:599-625) with HOST xo / out for small test sets:
+ * K(xo,xo) - Z Z^T, Z = K(xo,x) L^-T, W = L^-1 [roundup(n,128)]^2 (stage 2 above).
+ * scratch: DEVICE, 256-byte aligned, >= gpb_post_cov_scratch_doubles(m, n) doubles.           */
+size_t gpb_post_cov_scratch_doubles(int64_t m, int64_t n);
+int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int64_t m,
+                      const double* x, int64_t n, const double* W, int64_t ldw, double* scratch,
+                      double* out_host, int64_t ld_out, void* stream);
+
 /* ---- host-buffer drop-ins for the reference's Cython signatures ----------------
  * f(out, x1, x2, h, w[, p]) with caller-allocated C-contiguous out, exactly the
  * arguments of gaussian_c.pyx:18,39,44,51,72,95,116,139,143 and

@@ -9,7 +9,7 @@ from conftest import synth_xy
 x, y = synth_xy(1024, 0)
 e = engine.Engine(engine.GAUSSIAN, (1.0, 0.5), 1.0, x, y)
 for rep in range(3):
-    e._c.clear(); e.factor(); torch.cuda.synchronize()
+    e.reset(); e.factor(); torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
 _lib.lib.gpb_debug_diag_clk(buf)
 c = np.array(buf[:18], dtype=np.int64)

@@ -129,6 +129,49 @@ def test_gp_vs_oracle(oracle, n, kparams, s, m):
     assert gp.dm_dtheta(np.empty(0)).shape == (len(kparams) + 1, 0)
 
 
+@pytest.mark.parametrize("n", [3, 31, 32, 33, 50, 64, 65, 96, 97, 100])
+@pytest.mark.parametrize("kparams,s", [((1.1, 0.35), 0.6), ((0.9, 0.8, 1.4), 0.8)])
+def test_one_block_gp_vs_oracle(oracle, n, kparams, s):
+    """N <= 128: factor + invert in one CTA (identity sub-blocks skipped), then solves, log_lh,
+    K^-1 and the gradient brackets in ONE more launch (small.cu); every sub-block count and both
+    sides of each 32-boundary.  The gradient is asked for first (cold: one library call)."""
+    x, y = synth_xy(n, 100 + n)
+    xo = np.linspace(-6, 6, 37)
+    gp = GP(make_kernel(kparams), x, y, s=s)
+    o = oracle.OracleGP(kind_of(oracle, kparams), kparams, x, y, s)
+    assert_parity(gp.dloglh_dtheta, o.dloglh_dtheta, RTOL, "dloglh (cold)")
+    for key in ("log_lh", "inv_Kxx_y", "inv_Kxx", "Lxx", "dlh_dtheta"):
+        assert_parity(getattr(gp, key), getattr(o, key), RTOL, key)
+    assert_parity(gp.mean(xo), o.mean(xo), RTOL, "mean")
+    assert_parity(gp.cov(xo), o.cov(xo), RTOL, "cov")
+    assert_parity(gp.var(xo), np.diag(o.cov(xo)), RTOL, "var")
+    assert_parity(gp.dm_dtheta(xo), o.dm_dtheta(xo), RTOL, "dm")
+    assert_parity(gp.d2loglh_normalised(), o.d2lh_dtheta2_with(1.0, o.dloglh_dtheta), RTOL, "d2lh(lh=1)")
+    # same candidate through the batched evaluator (device KParams, batch > 1)
+    th = np.array(list(kparams) + [s])
+    llh, grad = gp.batch_eval(np.stack([th, th * 1.01, th]))
+    assert_parity(llh[0], o.log_lh) and assert_parity(grad[0], o.dloglh_dtheta)
+    assert llh[2] == llh[0] and np.array_equal(grad[2], grad[0])
+    # new hyperparameters on the resident engine
+    gp.set_param("w", kparams[1] * 1.3)
+    o2 = oracle.OracleGP(kind_of(oracle, kparams), (kparams[0], kparams[1] * 1.3) + tuple(kparams[2:]), x, y, s)
+    assert_parity(gp.log_lh, o2.log_lh) and assert_parity(gp.dloglh_dtheta, o2.dloglh_dtheta)
+
+
+def test_one_block_not_pd_and_clamp(oracle):
+    from suite_util import INVALID_X, INVALID_Y, INVALID_H, INVALID_W
+    gp = GP(GaussianKernel(INVALID_H, INVALID_W), INVALID_X, INVALID_Y, s=0)
+    assert np.isnan(gp.dloglh_dtheta).all() and gp.log_lh == -np.inf and gp.lh == 0
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.inv_Kxx
+    # logdet < MIN with a successful Cholesky: -inf, finite gradient (gp_c.pyx:22-23)
+    x, y = synth_xy(120, 3)
+    g2 = GP(GaussianKernel(1.0, 1.0), x, y, s=1e-2)           # cond(Kxx) = 1e5
+    o = oracle.OracleGP(oracle.GAUSSIAN, (1.0, 1.0), x, y, 1e-2)
+    assert o.log_lh == -np.inf and g2.log_lh == -np.inf
+    assert_parity(g2.dloglh_dtheta, o.dloglh_dtheta, 1e-7, "dloglh at s=1e-2")
+
+
 def test_logdet_clamp_matches_reference(oracle):
     """logdet(Kxx) < MIN -> log_lh = -inf although the Cholesky succeeds; the
     gradient is still finite (only LinAlgError gives NaN)."""
