@@ -515,13 +515,15 @@ static int eval_group(int kind, const double* thetas, int batch, const double* x
     // the factorisation reads the lower triangle only: skip the tiles above it (half the exp work)
     stt = gpb_launch_build(kind, nullptr, w.Pb, batch, x, n, x, n, np_, np_, outs, np_, mstride, 1, 1, st, 1);
     if (stt) return stt;
-    stt = gpb_launch_potrf(w.L, np_, np_, mstride, batch, w.W, np_, mstride, want_grad ? w.V : nullptr, np_, mstride, w.info, st, n);
+    const bool one_block = (np_ == GPB_NB);
+    stt = gpb_launch_potrf(w.L, np_, np_, mstride, batch, w.W, np_, mstride, want_grad ? w.V : nullptr, np_, mstride, w.info, st, n,
+                           !one_block);
     if (stt) return stt;
-    if (np_ == GPB_NB) {
+    if (one_block) {
         // one 128-block per candidate: solves, log_lh, K^-1 and the gradient brackets in ONE launch
         stt = gpb_launch_small_tail(kind, nullptr, w.Pb, batch, x, n, w.ypad, 0, w.L, np_, mstride, w.W, np_, mstride,
                                     want_grad ? w.Ki : nullptr, np_, mstride, w.z, w.alpha, np_, w.info, w.out3,
-                                    w.out8, st);
+                                    w.out8, w.W, want_grad ? w.V : nullptr, np_, mstride, nullptr, st);
         if (stt) return stt;
     } else {
         stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, mstride, mstride, batch, w.ypad, 0, w.z, w.alpha, np_, w.flags, st);
@@ -631,6 +633,7 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
     gpb_make_kparams(&P, kind, theta, theta[nkp]);
     int stt;
     unsigned done = 0;
+    bool packed = false;
     if (np_ == GPB_NB) {
         // a GP that fits one 128-block: build, factor + invert (one CTA), then everything else in
         // one more launch -- all four stages at once, whatever subset was asked for
@@ -639,12 +642,13 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
             outs[0] = w.L;
             stt = gpb_launch_build(kind, &P, nullptr, 1, x, n, x, n, np_, np_, outs, np_, 0, 1, 1, st, 1);
             if (stt) return stt;
-            stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n);
+            stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n, false);
             if (stt) return stt;
             stt = gpb_launch_small_tail(kind, &P, nullptr, 1, x, n, ypad, 0, w.L, np_, 0, w.W, np_, 0, w.Ki, np_, 0,
-                                        w.z, w.alpha, np_, w.info, w.out3, w.out8, st);
+                                        w.z, w.alpha, np_, w.info, w.out3, w.out8, w.W, w.V, np_, 0, w.pack, st);
             if (stt) return stt;
             done = 15u;
+            packed = true;
         }
         stages = 0;
     }
@@ -676,8 +680,10 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
     }
     done |= stages & 15u;
     if (host_out) {
-        stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, w.out8, w.info, w.pack);
-        GPB_LAUNCH_CHECK("stage_pack_kernel");
+        if (!packed) {
+            stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, w.out8, w.info, w.pack);
+            GPB_LAUNCH_CHECK("stage_pack_kernel");
+        }
         int slot;
         void* hp;
         stt = pin_acquire(GPB_STAGE_PACK * 8, &slot, &hp);
@@ -702,15 +708,27 @@ int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int
     const long long mr = roundup(m, 32);
     KParams P;
     gpb_make_kparams(&P, kind, theta, 0.0);
-    GPB_CUDA(cudaMemcpyAsync(scratch, xo_host, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    // small test sets go through a page-locked slot in both directions: a pageable cudaMemcpyAsync
+    // costs ~12 us per direction in the driver, the whole kernel runs ~4 us
+    const bool pinned = (size_t)m * 16 <= ((size_t)4 << 20);
+    int slot = -1;
+    void* hp = nullptr;
+    if (pinned) {
+        int stt = pin_acquire((size_t)m * 16, &slot, &hp);
+        if (stt) return stt;
+        memcpy(hp, xo_host, (size_t)m * 8);
+    }
+    GPB_CUDA(cudaMemcpyAsync(scratch, pinned ? hp : xo_host, (size_t)m * 8, cudaMemcpyHostToDevice, st));
     const int sl[1] = {0}, oi[1] = {0};
     const double cf[1] = {1.0};
     const double* vec[1] = {alpha};
     double* out[1] = {scratch + mr};
     int stt = gpb_launch_fused_matvec(kind, &P, nullptr, 1, scratch, m, x, n, 1, sl, oi, cf, vec, 1, out, 0, 0, st);
     if (stt) return stt;
-    GPB_CUDA(cudaMemcpyAsync(out_host, scratch + mr, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    double* dst = pinned ? (double*)hp + m : out_host;
+    GPB_CUDA(cudaMemcpyAsync(dst, scratch + mr, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
     GPB_CUDA(cudaStreamSynchronize(st));
+    if (pinned) memcpy(out_host, dst, (size_t)m * 8);
     return GPB_OK;
 }
 
@@ -738,7 +756,16 @@ int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int6
     double* C = Z + mp * np_;
     KParams P;
     gpb_make_kparams(&P, kind, theta, 0.0);
-    GPB_CUDA(cudaMemcpyAsync(dxo, xo_host, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    {
+        int slot;
+        void* hp;
+        int stt = pin_acquire((size_t)m * 8, &slot, &hp);
+        if (stt) return stt;
+        memcpy(hp, xo_host, (size_t)m * 8);
+        GPB_CUDA(cudaMemcpyAsync(dxo, hp, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        stt = pin_release(slot, st);
+        if (stt) return stt;
+    }
     double* outs[GPB_MAX_SLICES] = {nullptr};
     outs[0] = Kxox;
     int stt = gpb_launch_build(kind, &P, nullptr, 1, dxo, m, x, n, mp, np_, outs, np_, 0, 0, 0, st);

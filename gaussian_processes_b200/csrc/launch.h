@@ -61,7 +61,9 @@ int gpb_launch_post_var(int kind, const KParams* P, const double* Z, long long l
 // potrf.cu
 int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
-                     cudaStream_t st, long long n_valid = 0);   // n_valid: rows that are not identity pad (0 = n)
+                     cudaStream_t st, long long n_valid = 0, bool zero_blocks = true);
+// n_valid: rows that are not identity pad (0 = n); zero_blocks = false: the caller writes the structural
+// zeros of the inverted diagonal blocks itself (gpb_launch_small_tail does)
 int gpb_launch_trtri(const double* L, long long n, long long ld, long long sL, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, double* T,
                      long long ldt, long long sT, cudaStream_t st);
@@ -82,7 +84,11 @@ int gpb_launch_small_tail(int kind, const KParams* P, const KParams* Pb, int bat
                           const double* y, long long sy, const double* L, long long ldl, long long sL,
                           const double* W, long long ldw, long long sW, double* Ki, long long ldk, long long sK,
                           double* z, double* alpha, long long svec, const int* info, double* out3,
-                          double* out16, cudaStream_t st);
+                          double* out16, double* Wz, double* Vz, long long ldv, long long sV, double* pack,
+                          cudaStream_t st);
+// Wz / Vz (optional): W and V again, writable -- the kernel then writes their structural zeros (the
+// strictly upper / lower 32x32 sub-blocks) instead of a zero_diag_blocks launch.  pack (optional):
+// the 24-double read-back block of gpb_gp_stages for batch 1.
 
 // reduce.cu
 int gpb_launch_gemv(const double* A, long long rows, long long cols, long long lda, const double* x,

@@ -268,7 +268,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             double* Wo = Wd + bb * SBSZ;
 #pragma unroll
             for (int r = 0; r < SB; r++) Wo[r * SLD + lane] = w[r];
-        } else if (wid <= nbelow) {
+        } else if (wid <= nbelow && bb + wid < nsub) {      // (rows in the identity pad stay zero)
             // ---- P3 (warps 1..nbelow): sub-block (bb+wid, bb): X = A L_bb^-T, lane = row.
             //      The still unused inverse slot of that block row is the warp's private staging
             //      area, so every shared-memory access below is conflict-free.
@@ -308,6 +308,7 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             while ((ii + 1) * (ii + 2) / 2 <= pr) ii++;
             const int jj = pr - ii * (ii + 1) / 2;
             const int bi = bb + 1 + ii, bj = bb + 1 + jj;
+            if (bi >= nsub) continue;                 // L_ib = 0 in the identity pad: nothing to subtract
             double* Cb = Lb + blk(bi, bj) * SBSZ;
             const int cs = (bi == bj) ? DLD : SLD;
             double acc[2][4][2];
@@ -365,14 +366,14 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     if (wid < 4) {                                    // level 1a
         const int q = wid >> 1, hf = wid & 1, i = q ? 3 : 1, j = q ? 2 : 0;
         strip_zero(acc);
-        strip_mm(acc, Lb + blk(i, j) * SBSZ, Wd + j * SBSZ, hf, g, t, 1.0);
+        if (i < nsub) strip_mm(acc, Lb + blk(i, j) * SBSZ, Wd + j * SBSZ, hf, g, t, 1.0);   // else L_ij = 0
         strip_to_smem(acc, q ? dg1 : dg0, hf, g, t);
     }
     __syncthreads();
     if (wid < 4) {                                    // level 1b
         const int q = wid >> 1, hf = wid & 1, i = q ? 3 : 1, j = q ? 2 : 0;
         strip_zero(acc);
-        strip_mm(acc, Wd + i * SBSZ, q ? dg1 : dg0, hf, g, t, -1.0);
+        if (i < nsub) strip_mm(acc, Wd + i * SBSZ, q ? dg1 : dg0, hf, g, t, -1.0);
         strip_to_smem(acc, q ? W32 : W10, hf, g, t);
         strip_to_wv(acc, W, ldw, V, ldv, i, j, hf, g, t);
     }
@@ -381,7 +382,9 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
     {                                                 // level 2a: S_ij = sum_k L_ik W_kj, k = j..1
         const int i = 2 + (wid >> 2), j = (wid >> 1) & 1, hf = wid & 1;
         strip_zero(acc);
-        if (j == 0) {
+        if (i >= nsub) {
+            // block row i of L is zero left of the diagonal: S_ij = 0
+        } else if (j == 0) {
             strip_mm(acc, Lb + blk(i, 0) * SBSZ, Wd, hf, g, t, 1.0);
             strip_mm(acc, Lb + blk(i, 1) * SBSZ, W10, hf, g, t, 1.0);
         } else {
@@ -398,7 +401,9 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
         const double* S2 = j ? dg1 : dg0;
         const double* S3 = j ? Lb + blk(3, 2) * SBSZ : Lb + blk(1, 0) * SBSZ;
         strip_zero(acc);
-        if (i == 2) {
+        if (i >= nsub) {
+            // W_ij = 0
+        } else if (i == 2) {
             strip_mm(acc, Wd + 2 * SBSZ, S2, hf, g, t, -1.0);
         } else {
             strip_mm(acc, W32, S2, hf, g, t, -1.0);
@@ -671,7 +676,7 @@ extern "C" int gpb_debug_diag_clk(long long* out) {
 
 int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
-                     cudaStream_t st, long long n_valid) {
+                     cudaStream_t st, long long n_valid, bool zero_blocks) {
     GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
     GPB_REQUIRE(ld >= n && ldw >= n && (!V || ldv >= n), "leading dimension too small");
     if (n_valid <= 0 || n_valid > n) n_valid = n;
@@ -685,8 +690,10 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     }
     GPB_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
     const int T = (int)(n / GPB_NB);
-    zero_diag_blocks_kernel<<<dim3((unsigned)T, (unsigned)batch), 256, 0, st>>>(W, ldw, sW, V, ldv, sV);
-    GPB_LAUNCH_CHECK("zero_diag_blocks_kernel");
+    if (zero_blocks) {
+        zero_diag_blocks_kernel<<<dim3((unsigned)T, (unsigned)batch), 256, 0, st>>>(W, ldw, sW, V, ldv, sV);
+        GPB_LAUNCH_CHECK("zero_diag_blocks_kernel");
+    }
     // Two-level blocking: an outer panel of `inner` 128-columns is factored left-looking
     // (skinny column updates with K = q*128), then ONE trailing update with K = inner*128
     // touches the rest of the matrix -- half (or a quarter) as many passes over the trailing

@@ -39,6 +39,10 @@ struct TailArgs {
     const int* info;
     double* out3;           // [batch][3]
     double* out16;          // [batch][16]
+    double* Wz;             // optional: W / V again, writable: this kernel writes their structural zeros
+    double* Vz;
+    long long ldv, sV;
+    double* pack;           // optional (batch 1): {out3 | out16 | info | 0...}, the block gpb_gp_stages reads back
 };
 
 // acc (rows hf*16 .. +16 of a 32 x 32 block) += X Y with X[m][k] = xp[m*xsm + k*xsk],
@@ -84,12 +88,26 @@ __global__ void __launch_bounds__(256, 1) small_tail_kernel(const TailArgs a) {
     } else if (tid == 0) {
         sP = a.P;
     }
-    // ---- W (nn x nn, the structural zeros above the diagonal included) -> shared memory ----
+    // ---- W (nn x nn) -> shared memory; sub-blocks above the diagonal are structural zeros ----
     for (int e = tid; e < nn * (nn / 2); e += 256) {
         const int r = e / (nn / 2), c2 = (e % (nn / 2)) * 2;
-        cp_async16(Ws + r * TLD + c2, W + (long long)r * a.ldw + c2);
+        if (c2 / TB > r / TB) *reinterpret_cast<double2*>(Ws + r * TLD + c2) = make_double2(0.0, 0.0);
+        else cp_async16(Ws + r * TLD + c2, W + (long long)r * a.ldw + c2);
     }
     cp_async_commit();
+    if (a.Wz) {
+        // ... which this kernel also writes to global W (upper sub-blocks) and V = W^T (lower ones)
+        double* Wz = a.Wz + b * a.sW;
+        double* Vz = a.Vz ? a.Vz + b * a.sV : nullptr;
+        for (int e = tid; e < GPB_NB * (GPB_NB / 2); e += 256) {
+            const int r = e / (GPB_NB / 2), c2 = (e % (GPB_NB / 2)) * 2;
+            if (c2 / TB > r / TB) {
+                *reinterpret_cast<double2*>(Wz + (long long)r * a.ldw + c2) = make_double2(0.0, 0.0);
+            } else if (c2 / TB < r / TB && Vz) {
+                *reinterpret_cast<double2*>(Vz + (long long)r * a.ldv + c2) = make_double2(0.0, 0.0);
+            }
+        }
+    }
     if (tid < GPB_NB) {
         xs[tid] = (tid < n) ? a.x[tid] : 0.0;
         ys[tid] = (tid < n) ? y[tid] : 0.0;
@@ -141,6 +159,11 @@ __global__ void __launch_bounds__(256, 1) small_tail_kernel(const TailArgs a) {
         a.out3[b * 3 + 0] = llh;
         a.out3[b * 3 + 1] = logdet;
         a.out3[b * 3 + 2] = sq;
+        if (a.pack) {
+            a.pack[0] = llh; a.pack[1] = logdet; a.pack[2] = sq;
+            a.pack[19] = a.info ? (double)a.info[b] : 0.0;
+            for (int i = 20; i < 24; i++) a.pack[i] = 0.0;
+        }
     }
     if (!a.Ki) return;
 
@@ -215,6 +238,8 @@ __global__ void __launch_bounds__(256, 1) small_tail_kernel(const TailArgs a) {
         o[12] = tr;
         o[13] = saa;
         o[14] = o[15] = 0.0;
+        if (a.pack)
+            for (int i = 0; i < 16; i++) a.pack[3 + i] = o[i];
     }
 }
 
@@ -226,7 +251,8 @@ int gpb_launch_small_tail(int kind, const KParams* P, const KParams* Pb, int bat
                           const double* y, long long sy, const double* L, long long ldl, long long sL,
                           const double* W, long long ldw, long long sW, double* Ki, long long ldk, long long sK,
                           double* z, double* alpha, long long svec, const int* info, double* out3,
-                          double* out16, cudaStream_t st) {
+                          double* out16, double* Wz, double* Vz, long long ldv, long long sV, double* pack,
+                          cudaStream_t st) {
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(n >= 1 && n <= GPB_NB && batch >= 1, "small tail needs 1 <= n <= 128");
     GPB_REQUIRE(x && y && L && W && z && alpha && out3 && (!Ki || out16), "null pointer");
@@ -244,6 +270,8 @@ int gpb_launch_small_tail(int kind, const KParams* P, const KParams* Pb, int bat
     a.L = L; a.ldl = ldl; a.sL = sL; a.W = W; a.ldw = ldw; a.sW = sW;
     a.Ki = Ki; a.ldk = ldk; a.sK = sK; a.z = z; a.alpha = alpha; a.svec = svec;
     a.info = info; a.out3 = out3; a.out16 = out16;
+    a.Wz = Wz; a.Vz = Vz; a.ldv = ldv; a.sV = sV; a.pack = (batch == 1) ? pack : nullptr;
+    GPB_REQUIRE(!Vz || ((reinterpret_cast<uintptr_t>(Vz) & 15) == 0 && ldv % 2 == 0 && sV % 2 == 0), "V must be 16-byte aligned");
     GpbProfScope prof(GPB_KC_REDUCE, st);
     if (kind == GPB_GAUSSIAN) small_tail_kernel<GPB_GAUSSIAN><<<batch, 256, TAIL_SMEM, st>>>(a);
     else small_tail_kernel<GPB_PERIODIC><<<batch, 256, TAIL_SMEM, st>>>(a);
