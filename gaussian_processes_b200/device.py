@@ -41,6 +41,10 @@ def zeros(*shape):
     return torch.zeros(*shape, dtype=F64, device=require_cuda())
 
 
+def ones(*shape):
+    return torch.ones(*shape, dtype=F64, device=require_cuda())
+
+
 def izeros(*shape):
     return torch.zeros(*shape, dtype=torch.int32, device=require_cuda())
 

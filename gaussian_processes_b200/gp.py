@@ -174,9 +174,20 @@ class GP(object):
 
     # ------------------------------------------------------------------ device state
     def _engine(self):
-        """Device-side twin of the current (K, x, y, s); dropped by every setter."""
+        """Device-side twin of the current (K, x, y, s); dropped by every setter.  The built-in
+        kernels have fused CUDA functors (``KIND``); any other ``Kernel`` subclass evaluates its
+        matrices in its own Python methods and everything after that runs on the device."""
         kp = tuple(float(v) for v in self.K.params)
-        key = (type(self.K).KIND, kp, float(self._s))
+        kind = getattr(type(self.K), "KIND", None)
+        if kind is None:
+            key = (("host", id(self.K)), kp, float(self._s))
+            if self._dev is None or self._dev[0][0] != key[0]:
+                from .generic import HostKernelEngine
+                self._dev = (key, HostKernelEngine(self.K, key[2], self._x, self._y))
+            elif self._dev[0] != key:
+                self._dev = (key, self._dev[1].rebind(kp, key[2]))
+            return self._dev[1]
+        key = (kind, kp, float(self._s))
         if self._dev is None or self._dev[0][0] != key[0]:
             self._dev = (key, _engine.Engine(key[0], kp, key[2], self._x, self._y))
         elif self._dev[0] != key:           # same observations and kernel family, new hyperparameters

@@ -77,6 +77,18 @@ def batch_eval(gp, thetas, grad=True):
     thetas = np.ascontiguousarray(thetas, dtype=np.float64)
     if thetas.ndim != 2 or thetas.shape[1] != gp.params.size:
         raise ValueError("thetas must have shape [B, %d]" % gp.params.size)
+    if getattr(type(gp.K), "KIND", None) is None:
+        # user-defined kernel: its matrices come from Python methods, so candidates are evaluated one
+        # by one through the GP properties (the linear algebra of each still runs on the device)
+        trial = gp.copy()
+        llh = np.empty(thetas.shape[0])
+        g = np.empty(thetas.shape) if grad else None
+        for b, th in enumerate(thetas):
+            trial.params = th
+            llh[b] = trial.log_lh
+            if grad:
+                g[b] = trial.dloglh_dtheta
+        return llh, g
     llh, g, info = _evaluator(gp).eval(thetas, want_grad=grad)
     return llh, (g if grad else None)
 
@@ -190,6 +202,12 @@ def fit_MLII(gp, candidates, distributed=None, group=None, set_params=True, eval
     if distributed is None:
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized()
+    if evaluate is None and getattr(type(gp.K), "KIND", None) is None:
+        def evaluate(th):                       # user-defined kernel: per-candidate GP properties
+            l, g = batch_eval(gp, th)
+            bad = (~np.isfinite(l)).astype(np.float64)
+            t = torch.from_numpy(np.concatenate([l[:, None], g, bad[:, None]], axis=1))
+            return t.cuda() if torch.cuda.is_available() else t
     if evaluate is None:
         ev = _evaluator(gp)
 

@@ -439,3 +439,68 @@ def test_builders_large_and_skinny_downloads(oracle, n1, n2):
     assert_parity(k.jacobian(x1, x2), oracle.jacobian(oracle.GAUSSIAN, x1, x2, (1.1, 0.7)), RTOL, "jacobian")
     out = np.full((n1, n2), np.nan)
     assert k.dK_dw(x1, x2, out=out) is out and not np.isnan(out).any()
+
+
+# ------------------------------------------------------------------ user-defined kernels
+class NumpyGaussianKernel(gpb.Kernel):
+    """A user's own Kernel subclass (no CUDA functor): the Gaussian formulas of
+    gaussian_c.pyx:18-164 in numpy, so its GP must agree with the built-in kernel's."""
+    _names = ("h", "w")
+
+    def __init__(self, h, w):
+        self.set_param("h", h)
+        self.set_param("w", w)
+
+    def _parts(self, x1, x2):
+        d2 = (np.asarray(x1)[:, None] - np.asarray(x2)[None, :]) ** 2
+        c = np.sqrt(2.0 / np.pi)
+        return d2, c, np.exp(-0.5 * d2 / self.w ** 2)
+
+    def K(self, x1, x2, out=None):
+        d2, c, e = self._parts(x1, x2)
+        return 0.5 * c * self.h ** 2 / self.w * e
+
+    def jacobian(self, x1, x2, out=None):
+        d2, c, e = self._parts(x1, x2)
+        h, w = self.h, self.w
+        return np.stack([c * h / w * e, e * (0.5 * c * h ** 2 / w ** 4 * d2 - 0.5 * c * h ** 2 / w ** 2)])
+
+    def hessian(self, x1, x2, out=None):
+        d2, c, e = self._parts(x1, x2)
+        h, w = self.h, self.w
+        hh = c / w * e
+        hw = e * (c * h / w ** 4 * d2 - c * h / w ** 2)
+        ww = e * (0.5 * c * h ** 2 / w ** 7 * d2 ** 2 - 2.5 * c * h ** 2 / w ** 5 * d2 + c * h ** 2 / w ** 3)
+        return np.stack([np.stack([hh, hw]), np.stack([hw, ww])])
+
+
+@pytest.mark.parametrize("n,m", [(40, 25), (300, 130)])
+def test_user_defined_kernel_subclass(oracle, n, m):
+    """GP over a Kernel subclass that only exists in Python (gp.py calls K / jacobian / hessian on
+    whatever kernel object it is given): matrices from the user's methods, linear algebra on the
+    device; parity against the oracle's Gaussian GP on the same inputs."""
+    x, y = synth_xy(n, 5)
+    xo = np.linspace(-6, 6, m)
+    kp, s = (1.2, 0.45), 0.8
+    gp = GP(NumpyGaussianKernel(*kp), x, y, s=s)
+    o = oracle.OracleGP(oracle.GAUSSIAN, kp, x, y, s)
+    for key in ("Kxx", "Lxx", "inv_Kxx", "inv_Kxx_y", "log_lh", "dloglh_dtheta", "dlh_dtheta"):
+        assert_parity(getattr(gp, key), getattr(o, key), RTOL, key)
+    assert_parity(gp.mean(xo), o.mean(xo), RTOL, "mean")
+    assert_parity(gp.cov(xo), o.cov(xo), RTOL, "cov")
+    assert_parity(gp.var(xo), np.diag(o.cov(xo)), RTOL, "var")
+    assert_parity(gp.dm_dtheta(xo), o.dm_dtheta(xo), RTOL, "dm")
+    assert_parity(gp.d2loglh_normalised(), o.d2lh_dtheta2_with(1.0, o.dloglh_dtheta), RTOL, "d2lh(lh=1)")
+    # setters rebind the resident engine; copies and pickles keep working
+    gp.set_param("w", 0.6)
+    o2 = oracle.OracleGP(oracle.GAUSSIAN, (1.2, 0.6), x, y, s)
+    assert_parity(gp.log_lh, o2.log_lh)
+    assert_parity(gp.dloglh_dtheta, o2.dloglh_dtheta)
+    import pickle
+    g3 = pickle.loads(pickle.dumps(gp))
+    assert_parity(g3.mean(xo), o2.mean(xo))
+    cand = np.array([[1.2, 0.6, 0.8], [1.0, 0.5, 1.0]])
+    llh, grad = gp.batch_eval(cand)
+    assert_parity(llh[0], o2.log_lh) and assert_parity(grad[0], o2.dloglh_dtheta)
+    res = gp.fit_MLII(cand)
+    assert res.best_index == int(np.argmax(llh))
