@@ -315,6 +315,38 @@ def run_ours(args):
                      "note": "public API on a fitted GP (factor + L^-1 cached), host xo in, numpy out "
                              "(cov includes the D2H of the M x M result)"}
 
+    # ---- BASELINE configs[0], the reference's own CPU-runnable case: N=50, one GP object -------
+    # cold log_lh + dloglh_dtheta + mean + cov at 100 test points through the public API; the
+    # reference's path (oracle/_ref + scipy/numpy) timed beside it on the host cores
+    small = None
+    if rank == 0 and not args.no_posterior:
+        xs = np.linspace(-2 * np.pi, 2 * np.pi, 50)
+        ys, xos = np.sin(xs), np.linspace(-2 * np.pi, 2 * np.pi, 100)
+        gps = gpb.GP(gpb.GaussianKernel(1.0, 0.2), xs, ys, s=0)
+
+        def bundle(k):
+            gps.set_param("w", 0.2 + 1e-6 * (k + 1))            # setters drop every cached result (gp.py:231-240)
+            return gps.log_lh, gps.dloglh_dtheta, gps.mean(xos), gps.cov(xos)
+        for k in range(20):
+            bundle(k)
+        torch.cuda.synchronize()
+        reps = 200
+        t0 = time.perf_counter()
+        for k in range(reps):
+            bundle(100 + k)
+        t_b = (time.perf_counter() - t0) / reps
+        small = {"workload": "C1: N=50 GaussianKernel(1, 0.2), s=0: cold log_lh + dloglh_dtheta + mean + cov at 100 test points, one GP object",
+                 "ms_per_bundle": t_b * 1e3, "bundles_per_s": 1.0 / t_b,
+                 "launches_per_bundle": "2 (evaluation) + 1 (mean) + 4 (cov)", "host_syncs_per_bundle": 3}
+        if not args.no_cpu_baseline:
+            oracle = load_oracle()
+            impl = "ref" if oracle.have_ref() else "c"
+            t0 = time.perf_counter()
+            for k in range(reps):
+                o = oracle.OracleGP(oracle.GAUSSIAN, (1.0, 0.2 + 1e-6 * (k + 1)), xs, ys, 0.0, impl)
+                o.log_lh, o.dloglh_dtheta, o.mean(xos), o.cov(xos)
+            small["cpu_reference_ms_per_bundle"] = (time.perf_counter() - t0) / reps * 1e3
+
     if rank == 0:
         line = {
             "metric": "log_lh+dloglh_dtheta evals/sec at N=%d fp64" % n,
@@ -337,6 +369,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if posterior is not None:
             line["posterior"] = posterior
+        if small is not None:
+            line["small_gp"] = small
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
