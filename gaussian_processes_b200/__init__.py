@@ -14,10 +14,10 @@ needs a CUDA device.
 from . import _lib            # noqa: F401  (fails loudly when the CUDA library is missing)
 from . import ext
 from .gp import GP
-from .kernels import Kernel, PeriodicKernel, GaussianKernel
+from .kernels import Kernel, PeriodicKernel, GaussianKernel, SymbolicKernel
 from .mlii import fit_MLII, MLIIResult
 
-__all__ = ["ext", "GP", "Kernel", "PeriodicKernel", "GaussianKernel", "fit_MLII", "MLIIResult",
+__all__ = ["ext", "GP", "Kernel", "PeriodicKernel", "GaussianKernel", "SymbolicKernel", "fit_MLII", "MLIIResult",
            "install_as_gp"]
 __version__ = "0.1.0"
 

@@ -48,24 +48,59 @@ class HostKernelEngine(Engine):
     def _up(self, a, rows, cols, identity_pad=False):
         return D.mat_to_device(np.asarray(a, dtype=DTYPE), rows, cols, identity_pad=identity_pad)
 
-    def _host_K(self):
-        K = np.array(self.kernel(self.hx, self.hx), dtype=DTYPE)          # gp.py:264
-        K[np.diag_indices(self.n)] += self.s ** 2                         # gp.py:265 (index diagonal)
-        return K
+    # Kernel matrices on the device, zero padded to [rows, cols].  A kernel with generated CUDA
+    # functors (kernels/symbolic.py: ``device_slices``) builds them there; any other Kernel subclass
+    # evaluates them in its own Python methods and they are uploaded.
+    def _dev(self, xh):
+        return self.dx if xh is self.hx else D.to_device(xh)
+
+    def _mK(self, x1, x2, rows, cols):
+        if hasattr(self.kernel, "device_slices"):
+            return self.kernel.device_slices(self._dev(x1), x1.size, self._dev(x2), x2.size, rows, cols, 1)[0]
+        return self._up(self.kernel(x1, x2), rows, cols)
+
+    def _mJ(self, x1, x2, rows, cols):
+        n_p = self.n_p
+        if hasattr(self.kernel, "device_slices"):
+            J = self.kernel.device_slices(self._dev(x1), x1.size, self._dev(x2), x2.size, rows, cols,
+                                          ((1 << n_p) - 1) << 1)
+            return [J[i] for i in range(n_p)]
+        J = np.asarray(self.kernel.jacobian(x1, x2), dtype=DTYPE)
+        return [self._up(J[i], rows, cols) for i in range(n_p)]
+
+    def _mH(self, x1, x2, rows, cols):
+        """{(i, j): d2K_ij, j >= i} (the Hessian is symmetric in the parameter pair)."""
+        n_p = self.n_p
+        pairs = [(i, j) for i in range(n_p) for j in range(i, n_p)]
+        if hasattr(self.kernel, "device_slices"):
+            mask = sum(1 << (1 + n_p + i * n_p + j) for i, j in pairs)
+            H = self.kernel.device_slices(self._dev(x1), x1.size, self._dev(x2), x2.size, rows, cols, mask)
+            return {pr: H[q] for q, pr in enumerate(pairs)}          # slice order = ascending bit order
+        H = np.asarray(self.kernel.hessian(x1, x2), dtype=DTYPE)
+        return {(i, j): self._up(H[i, j], rows, cols) for i, j in pairs}
 
     def Kxx(self):
         if "K" not in self._c:
-            K = self._host_K()
-            if not np.isfinite(K).all():
-                raise ValueError("array must not contain infs or NaNs")      # scipy check_finite, gp.py:294
-            self._c["K"] = self._up(K, self.npad, self.npad, identity_pad=True)
+            n = self.npad
+            if hasattr(self.kernel, "device_slices"):
+                K = self.kernel.device_slices(self.dx, self.n, self.dx, self.n, n, n, 1, s2=self.s ** 2,
+                                              add_diag=True, pad_identity=True)[0]
+                import torch
+                finite = bool(torch.isfinite(K).all().item())
+            else:
+                Kh = np.array(self.kernel(self.hx, self.hx), dtype=DTYPE)          # gp.py:264
+                Kh[np.diag_indices(self.n)] += self.s ** 2                         # gp.py:265 (index diagonal)
+                finite = bool(np.isfinite(Kh).all())
+                K = self._up(Kh, n, n, identity_pad=True) if finite else None
+            if not finite:
+                raise ValueError("array must not contain infs or NaNs")            # scipy check_finite, gp.py:294
+            self._c["K"] = K
         return self._c["K"]
 
     def _jac(self):
         """dK_i(x, x), i < n_p, zero padded, on the device (gp.py:271)."""
         if "J" not in self._c:
-            J = np.asarray(self.kernel.jacobian(self.hx, self.hx), dtype=DTYPE)
-            self._c["J"] = [self._up(J[i], self.npad, self.npad) for i in range(self.n_p)]
+            self._c["J"] = self._mJ(self.hx, self.hx, self.npad, self.npad)
         return self._c["J"]
 
     # ------------------------------------------------------------------ staged chain
@@ -147,7 +182,7 @@ class HostKernelEngine(Engine):
         nth = n_p + 1
         Ki, a = self.Ki(), self.alpha()
         J = self._jac()
-        H = np.asarray(self.kernel.hessian(self.hx, self.hx), dtype=DTYPE)      # gp.py:276
+        H = self._mH(self.hx, self.hx, npad, npad)                              # gp.py:276
         B = [self.gemv(J[i], n, n, a, D.zeros(npad)) for i in range(n_p)]       # b_i = dK_i alpha
         C = [self.gemv(Ki, n, n, B[i], D.zeros(npad)) for i in range(n_p)]      # c_i = Ki b_i
         Kia = self.gemv(Ki, n, n, a, D.zeros(npad))
@@ -163,9 +198,8 @@ class HostKernelEngine(Engine):
                 dev["G", i, j] = self.dot(B[j], C[i], n)
                 dev["TP", i, j] = self._trace(P[j], P[i])
                 if j >= i:
-                    Hij = self._up(H[i, j], npad, npad)
-                    dev["Q", i, j] = self._quad(a, Hij, a)
-                    dev["TH", i, j] = self._trace(Ki, Hij)
+                    dev["Q", i, j] = self._quad(a, H[i, j], a)
+                    dev["TH", i, j] = self._trace(Ki, H[i, j])
             dev["Gs", i] = self.dot(a, C[i], n)
             dev["sG", i] = self.dot(B[i], Kia, n)
             dev["TPs", i] = self._trace(Ki, P[i])
@@ -201,7 +235,7 @@ class HostKernelEngine(Engine):
         m = int(xo.size)
         if m == 0:
             return np.empty(0, dtype=DTYPE)
-        Kxox = self._up(self.kernel(xo, self.hx), m, self.npad)                  # gp.py:572
+        Kxox = self._mK(xo, self.hx, m, self.npad)                               # gp.py:572
         return D.to_host(self.gemv(Kxox, m, self.n, a)).copy()                   # gp.py:597
 
     def cov(self, xo, host=True):
@@ -211,10 +245,10 @@ class HostKernelEngine(Engine):
         if m == 0:
             return np.empty((0, 0), dtype=DTYPE)
         mp = D.roundup(m)
-        Kxox = self._up(self.kernel(xo, self.hx), mp, self.npad)
+        Kxox = self._mK(xo, self.hx, mp, self.npad)
         Z = D.empty(mp, self.npad)
         self.gemm(Kxox, W, Z, mp, self.npad, self.npad, b_tri=1)
-        Cm = self._up(self.kernel(xo, xo), mp, mp)                               # gp.py:524
+        Cm = self._mK(xo, xo, mp, mp)                                            # gp.py:524
         self.gemm(Z, Z, Cm, mp, mp, self.npad, alpha=-1.0, beta=1.0, lower_only=1, Ct=Cm)
         if not host:
             return Cm[:m, :m]
@@ -237,13 +271,13 @@ class HostKernelEngine(Engine):
         if m == 0:
             return out
         J = self._jac()
-        Kxox = self._up(self.kernel(xo, self.hx), m, npad)
-        Jxo = np.asarray(self.kernel.jacobian(xo, self.hx), dtype=DTYPE)         # gp.py:656
+        Kxox = self._mK(xo, self.hx, m, npad)
+        Jxo = self._mJ(xo, self.hx, m, npad)                                     # gp.py:656
         res = D.zeros(nth, m)
         for i in range(n_p):
             b = self.gemv(J[i], n, n, a, D.zeros(npad))                          # dK_i alpha
             c = self.gemv(Ki, n, n, b, D.zeros(npad))                            # Ki dK_i alpha
-            self.gemv(self._up(Jxo[i], m, npad), m, n, a, res[i])                # dK_i(xo, x) alpha
+            self.gemv(Jxo[i], m, n, a, res[i])                                   # dK_i(xo, x) alpha
             self.gemv(Kxox, m, n, c, res[i], alpha=-1.0, beta=1.0)
         kia = self.gemv(Ki, n, n, a, D.zeros(npad))
         self.gemv(Kxox, m, n, kia, res[n_p], alpha=-2.0 * self.s)

@@ -199,3 +199,27 @@ def test_refine_batched_bfgs_on_analytic_surface():
         mlii.refine(np.array([[1.0, -1.0, 1.0]]), ev)
     th0, f0, g0, n0 = mlii.refine(np.empty((0, 3)), ev)
     assert th0.shape == (0, 3) and n0 == 0
+
+
+# ------------------------------------------------------------------ generated functors
+def test_symbolic_kernel_codegen_compiles_for_sm100a():
+    """sym_K -> CUDA source (K, Jacobian, Hessian with shared sub-expressions) -> NVRTC cubin for
+    sm_100a.  Compilation needs no GPU; running the builder does (tests/test_parity_gpu.py)."""
+    pytest.importorskip("sympy")
+    pytest.importorskip("cuda.bindings.nvrtc")
+    import sympy as sym
+    from gaussian_processes_b200 import GaussianKernel, PeriodicKernel, SymbolicKernel
+    from gaussian_processes_b200.kernels.symbolic import _Module
+    for k0 in (GaussianKernel(1.0, 0.5), PeriodicKernel(1.0, 0.5, 1.3)):
+        k = SymbolicKernel.from_kernel(k0)
+        assert (k.params == k0.params).all() and k._names == k0._names
+        assert "symk_eval2" in k.cuda_source and k.cuda_source.count("exp(") <= 3     # one exp per level
+        assert len(_Module.compile(k.cuda_source)) > 1000
+        assert (k.copy().params == k.params).all() and k.copy() is not k
+    h, w, a, d = sym.symbols("h w a d")
+    rq = SymbolicKernel(h ** 2 * (1 + d ** 2 / (2 * a * w ** 2)) ** (-a), ("h", "w", "a"), (1.0, 0.5, 2.0))
+    assert len(_Module.compile(rq.cuda_source)) > 1000
+    with pytest.raises(ValueError):
+        SymbolicKernel(h * sym.Symbol("zz") * d, ("h",), (1.0,))          # unknown symbol
+    with pytest.raises(ValueError):
+        rq.set_param("w", 0.0)                                             # same validation as the built-ins

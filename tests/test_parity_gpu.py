@@ -504,3 +504,65 @@ def test_user_defined_kernel_subclass(oracle, n, m):
     assert_parity(llh[0], o2.log_lh) and assert_parity(grad[0], o2.dloglh_dtheta)
     res = gp.fit_MLII(cand)
     assert res.best_index == int(np.argmax(llh))
+
+
+# ------------------------------------------------------------------ generated CUDA functors from sym_K
+@pytest.mark.parametrize("kparams", [(1.3, 0.4), (0.7, 0.9, 1.7)])
+def test_symbolic_kernel_builders_vs_oracle(oracle, kparams):
+    """The reference checks its Cython against sym_K (test_gaussian_kernel.py:67-88); here the code
+    generated FROM sym_K (NVRTC, sm_100a) is checked against the oracle's element loops."""
+    k = gpb.SymbolicKernel.from_kernel(make_kernel(kparams))
+    kind = kind_of(oracle, kparams)
+    rng = np.random.RandomState(3)
+    for n1, n2 in ((10, 10), (1, 7), (130, 67), (257, 300)):
+        x1, x2 = rng.uniform(-3, 3, n1), rng.uniform(-3, 3, n2)
+        assert_parity(k(x1, x2), oracle.K(kind, x1, x2, kparams), 1e-13, "K")
+        assert_parity(k.jacobian(x1, x2), oracle.jacobian(kind, x1, x2, kparams), 1e-12, "J")
+        assert_parity(k.hessian(x1, x2), oracle.hessian(kind, x1, x2, kparams), 1e-11, "H")
+    assert k(np.empty(0), x2).shape == (0, x2.size)
+
+
+@pytest.mark.parametrize("n,kparams", [(60, (1.2, 0.45)), (300, (1.2, 0.45)), (200, (0.9, 0.8, 1.4))])
+def test_gp_over_symbolic_kernel_vs_oracle(oracle, n, kparams):
+    """GP whose kernel matrices are built on the device by generated code; everything else the
+    library's kernels.  Parity against the oracle's GP for the same kernel function."""
+    x, y = synth_xy(n, 9)
+    xo = np.linspace(-6, 6, 70)
+    s = 0.8
+    gp = GP(gpb.SymbolicKernel.from_kernel(make_kernel(kparams)), x, y, s=s)
+    o = oracle.OracleGP(kind_of(oracle, kparams), kparams, x, y, s)
+    for key in ("Kxx", "Lxx", "inv_Kxx", "inv_Kxx_y", "log_lh", "dloglh_dtheta", "Kxx_J"):
+        assert_parity(getattr(gp, key), getattr(o, key), RTOL, key)
+    assert_parity(gp.mean(xo), o.mean(xo), RTOL, "mean")
+    assert_parity(gp.cov(xo), o.cov(xo), RTOL, "cov")
+    assert_parity(gp.dm_dtheta(xo), o.dm_dtheta(xo), RTOL, "dm")
+    assert_parity(gp.d2loglh_normalised(), o.d2lh_dtheta2_with(1.0, o.dloglh_dtheta), RTOL, "d2lh(lh=1)")
+
+
+def test_symbolic_kernel_new_function_vs_lambdified():
+    """A kernel the reference does not have (rational quadratic): generated builders against the
+    same sympy expressions evaluated by numpy, and the GP's log_lh / gradient against a direct
+    scipy computation."""
+    import sympy as sym
+    from scipy.linalg import cho_factor, cho_solve
+    h, w, a, d = sym.symbols("h w a d")
+    expr = h ** 2 * (1 + d ** 2 / (2 * a * w ** 2)) ** (-a)
+    vals = (1.1, 0.6, 1.7)
+    k = gpb.SymbolicKernel(expr, ("h", "w", "a"), vals)
+    x, y = synth_xy(150, 4)
+    D_ = x[:, None] - x[None, :]
+    f = sym.lambdify((d, h, w, a), expr, "numpy")
+    K = f(D_, *vals)
+    J = np.stack([sym.lambdify((d, h, w, a), sym.diff(expr, p), "numpy")(D_, *vals) for p in (h, w, a)])
+    assert_parity(k(x, x), K, 1e-13) and assert_parity(k.jacobian(x, x), J, 1e-12)
+    Hww = sym.lambdify((d, h, w, a), sym.diff(expr, w, w), "numpy")(D_, *vals)
+    assert_parity(k.hessian(x, x)[1, 1], Hww, 1e-11)
+    s = 0.7
+    gp = GP(k, x, y, s=s)
+    Kn = K + s ** 2 * np.eye(x.size)
+    cf = cho_factor(Kn, lower=True)
+    al = cho_solve(cf, y)
+    llh = -0.5 * y @ al - np.sum(np.log(np.diag(cf[0]))) - 0.5 * x.size * np.log(2 * np.pi)
+    Ki = cho_solve(cf, np.eye(x.size))
+    grad = [0.5 * al @ Ji @ al - 0.5 * np.sum(Ki * Ji) for Ji in J] + [s * (al @ al) - s * np.trace(Ki)]
+    assert_parity(gp.log_lh, llh) and assert_parity(gp.dloglh_dtheta, np.array(grad))
