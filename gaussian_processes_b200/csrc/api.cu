@@ -67,6 +67,7 @@ static GpbOption g_options[] = {
     {"gemm_bm", "GPB_GEMM_BM", 0, false},             // 64 (2 CTAs/SM) or 128 row tiles
     {"potrf_inner", "GPB_POTRF_INNER", 0, false},     // 128-columns per outer Cholesky panel
     {"potrf_lookahead", "GPB_POTRF_LOOKAHEAD", 0, false},   // 0 = panel look-ahead for one matrix of N >= 6144, 1 = always, 2 = off
+    {"potrf_panel_rl", "GPB_POTRF_PANEL_RL", 0, false},     // 0 = right-looking panel steps for one matrix, 1 = always, 2 = never
     {"gemm_impl", "GPB_GEMM_IMPL", 0, false},         // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
 };
 int gpb_get_option(const char* name) {
@@ -397,7 +398,8 @@ int gpb_post_var(int kind, const double* theta, const double* Z, int64_t ldz, in
 
 int gpb_potrf(double* A, int64_t n, int64_t ld, int64_t stride_a, int batch, double* W, int64_t ldw,
               int64_t stride_w, double* V, int64_t ldv, int64_t stride_v, int* info, void* stream) {
-    return gpb_launch_potrf(A, n, ld, stride_a, batch, W, ldw, stride_w, V, ldv, stride_v, info, S(stream));
+    return gpb_launch_potrf(A, n, ld, stride_a, batch, W, ldw, stride_w, V, ldv, stride_v, info, S(stream), 0, true,
+                            batch == 1);
 }
 
 int gpb_potrs(const double* L, const double* W, int64_t n, int64_t ld, int64_t ldw, int64_t stride_l,
@@ -657,7 +659,7 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
         outs[0] = w.L;
         stt = gpb_launch_build(kind, &P, nullptr, 1, x, n, x, n, np_, np_, outs, np_, 0, 1, 1, st, 1);
         if (stt) return stt;
-        stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n);
+        stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n, true, true);
         if (stt) return stt;
         stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, 0, 0, 1, ypad, 0, w.z, w.alpha, np_, w.flags, st);
         if (stt) return stt;

@@ -61,9 +61,10 @@ int gpb_launch_post_var(int kind, const KParams* P, const double* Z, long long l
 // potrf.cu
 int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
-                     cudaStream_t st, long long n_valid = 0, bool zero_blocks = true);
+                     cudaStream_t st, long long n_valid = 0, bool zero_blocks = true, bool single_chain = false);
 // n_valid: rows that are not identity pad (0 = n); zero_blocks = false: the caller writes the structural
-// zeros of the inverted diagonal blocks itself (gpb_launch_small_tail does)
+// zeros of the inverted diagonal blocks itself (gpb_launch_small_tail does); single_chain: one matrix whose
+// factorisation is not overlapped with others (right-looking panel steps, see potrf.cu)
 int gpb_launch_trtri(const double* L, long long n, long long ld, long long sL, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, double* T,
                      long long ldt, long long sT, cudaStream_t st);

@@ -676,7 +676,7 @@ extern "C" int gpb_debug_diag_clk(long long* out) {
 
 int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, int* info,
-                     cudaStream_t st, long long n_valid, bool zero_blocks) {
+                     cudaStream_t st, long long n_valid, bool zero_blocks, bool single_chain) {
     GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
     GPB_REQUIRE(ld >= n && ldw >= n && (!V || ldv >= n), "leading dimension too small");
     if (n_valid <= 0 || n_valid > n) n_valid = n;
@@ -718,6 +718,12 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
         GPB_CUDA(cudaStreamCreateWithPriority(&la_stream, cudaStreamNonBlocking, hi));
         for (auto& e : la_ev) GPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    // One matrix on its own (single_chain: the GP-object chain and the public gpb_potrf with batch 1): the
+    // panel steps are a serial chain of kernel latencies -> right-looking inside the panel.  The batched
+    // evaluator never sets it, so a candidate's arithmetic does not depend on how the batch was grouped.
+    // (option potrf_panel_rl: 0 = as the caller says, 1 = always, 2 = never)
+    const int rl_opt = gpb_get_option("potrf_panel_rl");
+    const bool panel_rl = (rl_opt == 1) || (rl_opt == 0 && single_chain && batch == 1);
     cudaStream_t ps = lookahead ? la_stream : st;
     cudaEvent_t ev_start = la_ev[0], ev_panel = la_ev[1], ev_b = la_ev[2], ev_end = la_ev[3];
     bool have_b = false;
@@ -731,7 +737,7 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
         for (int q = 0; q < kw; q++) {
             const int k = k0 + q;
             const long long o = (long long)k * GPB_NB;
-            if (q > 0) {                               // A[k:, k] -= L[k:, k0..k) * L[k, k0..k)^T
+            if (q > 0 && !panel_rl) {                  // A[k:, k] -= L[k:, k0..k) * L[k, k0..k)^T
                 GpbGemm c = gpb_gemm_default();
                 c.A = A + o * ld + p0; c.lda = ld; c.sA = sA;
                 c.B = A + o * ld + p0; c.ldb = ld; c.sB = sA;
@@ -761,6 +767,19 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
             g.b_tri = 1;                               // W_kk lower: k <= j
             int stt = gpb_launch_gemm(g, batch, ps);
             if (stt != GPB_OK) return stt;
+            const int ncols = (kw - 1 - q) * GPB_NB;
+            if (panel_rl && ncols > 0) {
+                // right-looking inside the panel: the new column updates the panel's remaining columns at
+                // once (K = 128), so no step of the serial chain carries a K = q*128 product
+                GpbGemm r = gpb_gemm_default();
+                r.A = A + (o + GPB_NB) * ld + o; r.lda = ld; r.sA = sA;
+                r.B = A + (o + GPB_NB) * ld + o; r.ldb = ld; r.sB = sA;
+                r.C = A + (o + GPB_NB) * ld + (o + GPB_NB); r.ldc = ld; r.sC = sA;
+                r.M = rem; r.N = ncols; r.K = GPB_NB;
+                r.alpha = -1.0; r.beta = 1.0;
+                stt = gpb_launch_gemm(r, batch, ps);
+                if (stt != GPB_OK) return stt;
+            }
         }
         const long long t0 = (long long)(k0 + kw) * GPB_NB;
         const int rem2 = (T - k0 - kw) * GPB_NB;
