@@ -108,6 +108,23 @@ static int pin_release(int slot, cudaStream_t st) {
     return GPB_OK;
 }
 
+// one persistent, grow-only page-locked buffer for the synchronous host-buffer posterior calls
+// (the ring above re-allocates a slot whenever a request outgrows it: ~1 ms per MB)
+static void* g_post_pin = nullptr;
+static size_t g_post_pin_cap = 0;
+static int post_pin_reserve(size_t bytes, void** host) {
+    if (bytes > g_post_pin_cap) {
+        if (g_post_pin) GPB_CUDA(cudaFreeHost(g_post_pin));
+        g_post_pin = nullptr; g_post_pin_cap = 0;
+        size_t cap = (size_t)1 << 16;
+        while (cap < bytes) cap <<= 1;
+        GPB_CUDA(cudaHostAlloc(&g_post_pin, cap, cudaHostAllocDefault));
+        g_post_pin_cap = cap;
+    }
+    *host = g_post_pin;
+    return GPB_OK;
+}
+
 // ---- internal streams for concurrent candidate groups ---------------------------------
 #define GPB_MAX_GROUPS 8
 static cudaStream_t g_gstream[GPB_MAX_GROUPS];
@@ -686,9 +703,8 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
             stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, w.out8, w.info, w.pack);
             GPB_LAUNCH_CHECK("stage_pack_kernel");
         }
-        int slot;
         void* hp;
-        stt = pin_acquire(GPB_STAGE_PACK * 8, &slot, &hp);
+        stt = post_pin_reserve(GPB_STAGE_PACK * 8, &hp);
         if (stt) return stt;
         GPB_CUDA(cudaMemcpyAsync(hp, w.pack, GPB_STAGE_PACK * 8, cudaMemcpyDeviceToHost, st));
         GPB_CUDA(cudaStreamSynchronize(st));
@@ -712,11 +728,10 @@ int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int
     gpb_make_kparams(&P, kind, theta, 0.0);
     // small test sets go through a page-locked slot in both directions: a pageable cudaMemcpyAsync
     // costs ~12 us per direction in the driver, the whole kernel runs ~4 us
-    const bool pinned = (size_t)m * 16 <= ((size_t)4 << 20);
-    int slot = -1;
+    const bool pinned = (size_t)m * 16 <= ((size_t)64 << 20);
     void* hp = nullptr;
     if (pinned) {
-        int stt = pin_acquire((size_t)m * 16, &slot, &hp);
+        int stt = post_pin_reserve((size_t)m * 16, &hp);
         if (stt) return stt;
         memcpy(hp, xo_host, (size_t)m * 8);
     }
@@ -759,14 +774,11 @@ int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int6
     KParams P;
     gpb_make_kparams(&P, kind, theta, 0.0);
     {
-        int slot;
         void* hp;
-        int stt = pin_acquire((size_t)m * 8, &slot, &hp);
+        int stt = post_pin_reserve((size_t)m * 8, &hp);      // the call synchronises before it returns
         if (stt) return stt;
         memcpy(hp, xo_host, (size_t)m * 8);
         GPB_CUDA(cudaMemcpyAsync(dxo, hp, (size_t)m * 8, cudaMemcpyHostToDevice, st));
-        stt = pin_release(slot, st);
-        if (stt) return stt;
     }
     double* outs[GPB_MAX_SLICES] = {nullptr};
     outs[0] = Kxox;

@@ -39,6 +39,47 @@ __device__ __forceinline__ void load_kparams(KParams* sP, const KParams& byval, 
 }
 
 // block (32, 8): each thread owns 2 adjacent columns and 4 rows (stride 8) of a 32 x 64 tile.
+// K only (slice 0), the common case (Kxx for the factorisation, K(xo, x), K(xo, xo)): no slice loop, the
+// eight separations of a thread evaluated together.  The generic kernel below spends ~100 issued
+// instructions per element on slice bookkeeping (ncu: FP64 pipe 38 % active); this one ~35.
+template <int KIND>
+__global__ void __launch_bounds__(256) build_k_kernel(const BuildArgs a) {
+    __shared__ KParams sP;
+    load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
+    if (a.lower_only && blockIdx.x > blockIdx.y / 2) return;
+    const long long j0 = ((long long)blockIdx.x * 32 + threadIdx.x) * 2;
+    if (j0 >= a.cols) return;
+    const bool ja = j0 < a.n2, jb = j0 + 1 < a.n2;
+    const double xa = ja ? a.x2[j0] : 0.0, xb = jb ? a.x2[j0 + 1] : 0.0;
+    double* o = a.out[0] + (long long)blockIdx.z * a.bstride;
+    const long long i0 = (long long)blockIdx.y * 32 + threadIdx.y;
+    double d[8], u[8][10];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const long long i = i0 + 8 * r;
+        const double xi = (i < a.n1) ? a.x1[i] : 0.0;
+        d[2 * r] = xi - xa;
+        d[2 * r + 1] = xi - xb;
+    }
+    gpb_eval_unique_v<KIND, 8>(sP, d, 1u, u);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const long long i = i0 + 8 * r;
+        if (i >= a.rows) break;
+        const bool vi = i < a.n1;
+        double v0 = (vi && ja) ? u[2 * r][0] : 0.0, v1 = (vi && jb) ? u[2 * r + 1][0] : 0.0;
+        if (a.add_diag) {
+            if (vi && ja && i == j0) v0 += sP.s2;
+            if (vi && jb && i == j0 + 1) v1 += sP.s2;
+        }
+        if (a.pad_identity) {
+            if (!(vi && ja) && i == j0) v0 = 1.0;
+            if (!(vi && jb) && i == j0 + 1) v1 = 1.0;
+        }
+        *reinterpret_cast<double2*>(o + i * a.ld + j0) = make_double2(v0, v1);
+    }
+}
+
 template <int KIND, bool VEC2>
 __global__ void __launch_bounds__(256) build_kernel(const BuildArgs a) {
     __shared__ KParams sP;
@@ -125,7 +166,12 @@ int gpb_launch_build(int kind, const KParams* P, const KParams* Pb, int batch, c
     dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 31) / 32), (unsigned)batch);
     GPB_REQUIRE(grid.y <= 65535 && batch <= 65535, "extent too large for the launch grid");
     GpbProfScope prof(GPB_KC_BUILD, st);
-    if (kind == GPB_GAUSSIAN) {
+    bool k_only = vec && a.out[0] != nullptr;
+    for (int s = 1; s < GPB_MAX_SLICES; s++) k_only = k_only && a.out[s] == nullptr;
+    if (k_only) {
+        if (kind == GPB_GAUSSIAN) build_k_kernel<GPB_GAUSSIAN><<<grid, block, 0, st>>>(a);
+        else build_k_kernel<GPB_PERIODIC><<<grid, block, 0, st>>>(a);
+    } else if (kind == GPB_GAUSSIAN) {
         if (vec) build_kernel<GPB_GAUSSIAN, true><<<grid, block, 0, st>>>(a);
         else build_kernel<GPB_GAUSSIAN, false><<<grid, block, 0, st>>>(a);
     } else {
@@ -215,11 +261,13 @@ __global__ void __launch_bounds__(256) mean_kernel(const MatvecArgs a) {
         for (long long c = 2 * lane; c < n2v; c += 64) {
             const double2 xc = *reinterpret_cast<const double2*>(a.x2 + c);
             const double2 vc = *reinterpret_cast<const double2*>(vec + c);
-            double u[10];
-            gpb_eval_unique<KIND>(sP, xa - xc.x, 1u, u); acc_a = fma(u[0], vc.x, acc_a);
-            gpb_eval_unique<KIND>(sP, xa - xc.y, 1u, u); acc_a = fma(u[0], vc.y, acc_a);
-            gpb_eval_unique<KIND>(sP, xb - xc.x, 1u, u); acc_b = fma(u[0], vc.x, acc_b);
-            gpb_eval_unique<KIND>(sP, xb - xc.y, 1u, u); acc_b = fma(u[0], vc.y, acc_b);
+            double u[4][10];
+            const double dd[4] = {xa - xc.x, xa - xc.y, xb - xc.x, xb - xc.y};
+            gpb_eval_unique_v<KIND, 4>(sP, dd, 1u, u);
+            acc_a = fma(u[0][0], vc.x, acc_a);
+            acc_a = fma(u[1][0], vc.y, acc_a);
+            acc_b = fma(u[2][0], vc.x, acc_b);
+            acc_b = fma(u[3][0], vc.y, acc_b);
         }
         for (long long c = n2v + lane; c < a.n2; c += 32) {
             double u[10];

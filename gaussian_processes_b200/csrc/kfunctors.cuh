@@ -76,6 +76,59 @@ inline void gpb_make_kparams(KParams* P, int kind, const double* theta, double s
 
 #ifdef __CUDACC__
 
+// exp for the kernel functors.  libdevice's exp() rebuilds its 11 polynomial coefficients from
+// 64-bit immediates on every call (two MOV/UMOV per coefficient: cuobjdump of the previous build showed
+// ~115 issued instructions per kernel-matrix element of which 24 were FP64), so the element kernels were
+// bound by instruction issue, not by the FP64 pipe.  Here the coefficients are constant-bank operands of the
+// DFMAs themselves: k = rint(x log2 e) by the 1.5*2^52 shift, two-term Cody-Waite reduction
+// r = x - k ln2 (|r| <= 0.3466), degree-13 Taylor/Horner (truncation 4e-18 relative), 2^k added straight
+// into the exponent field.  Valid while the result is a normal number; arguments outside (-700, 700)
+// (or NaN) take the library routine.  Max error measured against libm over the Gaussian / periodic
+// argument ranges: < 1 ulp (tests/test_parity_gpu.py keeps the 1e-13 builder tolerance).
+static __constant__ double gpb_exp_c[16] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0,
+    1.4426950408889634074, 6755399441055744.0};
+static __constant__ double gpb_exp_ln2[2] = {-6.93147180559945286227e-01, -2.31904681384629955842e-17};
+
+// W independent arguments at once: the Horner steps run coefficient-major, so each coefficient is
+// fetched once per W DFMAs (the element kernels evaluate 2-8 independent separations per thread).
+template <int W>
+__device__ __forceinline__ void gpb_expv(const double (&x)[W], double (&e)[W]) {
+    double r[W], p[W];
+    int k[W];
+    bool slow = false;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        slow |= !(fabs(x[w]) < 700.0);
+        const double t = fma(x[w], gpb_exp_c[14], gpb_exp_c[15]);
+        k[w] = __double2loint(t);
+        const double kf = t - gpb_exp_c[15];
+        r[w] = fma(kf, gpb_exp_ln2[1], fma(kf, gpb_exp_ln2[0], x[w]));
+        p[w] = gpb_exp_c[0];
+    }
+#pragma unroll
+    for (int i = 1; i < 14; i++) {
+        const double c = gpb_exp_c[i];
+#pragma unroll
+        for (int w = 0; w < W; w++) p[w] = fma(p[w], r[w], c);
+    }
+#pragma unroll
+    for (int w = 0; w < W; w++) e[w] = __hiloint2double(__double2hiint(p[w]) + (k[w] << 20), __double2loint(p[w]));
+    if (slow) {                      // rare: result not a normal number (or NaN / inf argument)
+#pragma unroll
+        for (int w = 0; w < W; w++)
+            if (!(fabs(x[w]) < 700.0)) e[w] = exp(x[w]);
+    }
+}
+
+__device__ __forceinline__ double gpb_exp(double x) {
+    const double xv[1] = {x};
+    double ev[1];
+    gpb_expv<1>(xv, ev);
+    return ev[0];
+}
+
 // u[idx] for a run-time idx without spilling u[] to local memory
 __device__ __forceinline__ double gpb_pick(const double* u, int idx) {
     double v = 0.0;
@@ -93,7 +146,7 @@ __device__ __forceinline__ void gpb_eval_unique(const KParams& P, double d, unsi
         const double d2 = d * d;
         const double e = P.c1 * d2;
         // entries whose exponent is below MIN are exactly 0 in every slice (gaussian_c.pyx:33-34)
-        const double ex = (e < GPB_MIN_LOG) ? 0.0 : exp(e);
+        const double ex = (e < GPB_MIN_LOG) ? 0.0 : gpb_exp(e);
         if (need & 1u) u[0] = P.k0 * ex;
         if (need & 2u) u[1] = P.j[0][0] * ex;
         if (need & 4u) u[2] = ex * (P.j[1][0] * d2 - P.j[1][1]);
@@ -104,7 +157,7 @@ __device__ __forceinline__ void gpb_eval_unique(const KParams& P, double d, unsi
         double S, C;
         sincos(d * P.half_ip, &S, &C);
         const double S2 = S * S;
-        const double E = exp(P.c1 * S2);
+        const double E = gpb_exp(P.c1 * S2);
         if (need & 1u) u[0] = P.k0 * E;
         if (need & 2u) u[1] = P.j[0][0] * E;
         const double ES2 = E * S2;
@@ -120,6 +173,38 @@ __device__ __forceinline__ void gpb_eval_unique(const KParams& P, double d, unsi
             const double C2 = C * C;
             u[9] = P.h[5][0] * (d * d) * E * (S2 - C2 + P.h[5][1] * S2 * C2) - P.h[5][2] * dESC;
         }
+    }
+}
+
+// W separations at once (same arithmetic per element as gpb_eval_unique, shared coefficient fetches)
+template <int KIND, int W>
+__device__ __forceinline__ void gpb_eval_unique_v(const KParams& P, const double (&d)[W], unsigned need,
+                                                  double (&u)[W][10]) {
+    if (KIND == GPB_GAUSSIAN) {
+        double e[W], ex[W], d2[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            d2[w] = d[w] * d[w];
+            const double ee = P.c1 * d2[w];
+            e[w] = (ee < GPB_MIN_LOG) ? 0.0 : ee;            // placeholder argument; zeroed below
+            ex[w] = ee;
+        }
+        double ev[W];
+        gpb_expv<W>(e, ev);
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            // entries whose exponent is below MIN are exactly 0 in every slice (gaussian_c.pyx:33-34)
+            const double x_ = (ex[w] < GPB_MIN_LOG) ? 0.0 : ev[w];
+            if (need & 1u) u[w][0] = P.k0 * x_;
+            if (need & 2u) u[w][1] = P.j[0][0] * x_;
+            if (need & 4u) u[w][2] = x_ * (P.j[1][0] * d2[w] - P.j[1][1]);
+            if (need & 8u) u[w][3] = P.h[0][0] * x_;
+            if (need & 16u) u[w][4] = x_ * (P.h[1][0] * d2[w] - P.h[1][1]);
+            if (need & 32u) u[w][5] = x_ * (P.h[2][0] * (d2[w] * d2[w]) - P.h[2][1] * d2[w] + P.h[2][2]);
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; w++) gpb_eval_unique<KIND>(P, d[w], need, u[w]);
     }
 }
 
