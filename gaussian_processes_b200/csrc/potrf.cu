@@ -58,6 +58,20 @@ constexpr int DIAG_SMEM = ((NBLK + 4) * SBSZ + SB + 2 * SB) * 8;   // L blocks, 
 
 __device__ __forceinline__ int blk(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
 
+// 1/sqrt(x) for a positive, normal pivot: MUFU.RSQ64H (2^-22.9) + one third-order correction
+// (error ~ e^3 = 2^-66).  libdevice's rsqrt() adds a special-value path behind a CALL; in the fully
+// unrolled sweep that call costs a register spill + reload and a BRA.DIV convergence check per
+// column, all on the serial pivot chain (cuobjdump of the previous build).  Pivots that are not
+// positive normal numbers are reported as a failed factorisation by the caller instead.
+__device__ __forceinline__ double rsqrt_pivot(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
+// smallest pivot taken as positive definite (far below anything a kernel matrix + s^2 I produces)
+#define GPB_PIVOT_MIN 1e-290
+
 // optional phase timing of the diagonal-block kernel (build with -DGPB_DIAG_CLK; read back with
 // gpb_debug_diag_clk): clock64 stamps of CTA 0 / thread 0 at the phase boundaries.
 #ifdef GPB_DIAG_CLK
@@ -208,36 +222,47 @@ potrf_diag_kernel(double* A, long long ld, long long sA, double* W, long long ld
             for (int k = 0; k < SB; k++) row[k] = Ld[lane * DLD + k];
             int fail = 0;
             double myinv = 0.0;
+            // Software-pipelined sweep: column k's critical part (pivot -> rsqrt -> scale -> the two rows
+            // the next two pivots need, by shuffle) is issued BEFORE the bulk update of column k-1
+            // (columns >= k+2, through the shared-memory broadcast), so the bulk FMAs and the
+            // store -> load round trip fill the latency of the serial chain instead of extending it.
+            // The next pivot is formed in lane k+1 from its own values (no wait for the row shuffle).
+            double piv = __shfl_sync(0xffffffffu, row[0], 0);
+            double lprev = 0.0;
 #pragma unroll
             for (int k = 0; k < SB; k++) {
-                const double piv = __shfl_sync(0xffffffffu, row[k], k);
-                if (!(piv > 0.0) && fail == 0) fail = k + 1;       // not positive definite (or NaN)
-                // 1/sqrt then one multiply: half the dependent latency of sqrt + divide on the
-                // critical path of the column sweep (|error| <= 2 ulp, far inside the 1e-9 parity)
-                const double id = rsqrt(piv);
+                if (!(piv > GPB_PIVOT_MIN) && fail == 0) fail = k + 1;   // not positive definite (or NaN)
+                const double id = rsqrt_pivot(piv);
                 const double d = piv * id;
                 const double lik = (lane == k) ? d : row[k] * id;
                 if (lane == k) myinv = id;
                 row[k] = lik;
                 if (k + 1 < SB) {
-                    // the next pivot needs only l_{k+1,k}: one shuffle keeps the serial chain short;
-                    // the rest of column k reaches the lanes through a shared-memory broadcast
-                    // (one 128-bit load per two columns instead of four shuffles)
+                    const double own = fma(-lik, lik, row[k + 1]);          // valid in lane k+1: next pivot
+                    piv = __shfl_sync(0xffffffffu, own, k + 1);
                     const double lnext = __shfl_sync(0xffffffffu, lik, k + 1);
                     row[k + 1] = fma(-lik, lnext, row[k + 1]);
                 }
                 if (k + 2 < SB) {
-                    double* cb = colbuf + (k & 1) * SB;
-                    cb[lane] = lik;
+                    const double lnext2 = __shfl_sync(0xffffffffu, lik, k + 2);
+                    row[k + 2] = fma(-lik, lnext2, row[k + 2]);
+                }
+                if (k >= 1 && k + 2 < SB) {
+                    // bulk update of column k-1: rows' elements j >= k+2
+                    const double* cb = colbuf + ((k - 1) & 1) * SB;
                     __syncwarp();
-                    if ((k + 2) & 1) row[k + 2] = fma(-lik, cb[k + 2], row[k + 2]);
+                    if ((k + 2) & 1) row[k + 2] = fma(-lprev, cb[k + 2], row[k + 2]);
 #pragma unroll
                     for (int j = (k + 3) & ~1; j + 1 < SB; j += 2) {
                         const double2 v = *reinterpret_cast<const double2*>(cb + j);
-                        row[j] = fma(-lik, v.x, row[j]);
-                        row[j + 1] = fma(-lik, v.y, row[j + 1]);
+                        row[j] = fma(-lprev, v.x, row[j]);
+                        row[j + 1] = fma(-lprev, v.y, row[j + 1]);
                     }
                 }
+                // column k for the next iteration's bulk update (this buffer was last read two
+                // iterations ago, with a __syncwarp in between)
+                if (k + 3 < SB) colbuf[(k & 1) * SB + lane] = lik;
+                lprev = lik;
             }
 #pragma unroll
             for (int k = 0; k < SB; k++) Ld[lane * DLD + k] = (k <= lane) ? row[k] : 0.0;
