@@ -748,7 +748,9 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
     // evaluator never sets it, so a candidate's arithmetic does not depend on how the batch was grouped.
     // (option potrf_panel_rl: 0 = as the caller says, 1 = always, 2 = never)
     const int rl_opt = gpb_get_option("potrf_panel_rl");
-    const bool panel_rl = (rl_opt == 1) || (rl_opt == 0 && single_chain && batch == 1);
+    // Up to N = 8192 only: the K = 128 updates are HBM-bound (6 flop/B), and once the panel is tall the
+    // three extra passes over it cost more than the shorter chain saves (N = 32768: 355 -> 397 ms).
+    const bool panel_rl = (rl_opt == 1) || (rl_opt == 0 && single_chain && batch == 1 && T <= 64);
     cudaStream_t ps = lookahead ? la_stream : st;
     cudaEvent_t ev_start = la_ev[0], ev_panel = la_ev[1], ev_b = la_ev[2], ev_end = la_ev[3];
     bool have_b = false;

@@ -245,9 +245,15 @@ def c4():
     t0 = time.perf_counter()
     res = gp.fit_MLII(cand, set_params=False)
     torch.cuda.synchronize()
+    dt_first = maxtime(time.perf_counter() - t0)              # includes growing the workspace to the full chunk size
+    sync()
+    t0 = time.perf_counter()
+    res = gp.fit_MLII(cand, set_params=False)
+    torch.cuda.synchronize()
     dt = maxtime(time.perf_counter() - t0)
     out = dict(config="C4", n=n, restarts=B, value=B / dt, metric="candidate evals/s (log_lh+grad), whole job",
-               seconds=dt, best_index=res.best_index, best_log_lh=float(res.best_log_lh))
+               seconds=dt, first_call_seconds=dt_first, first_call_value=B / dt_first,
+               best_index=res.best_index, best_log_lh=float(res.best_log_lh))
     if RANK == 0:
         oracle = load_oracle()
         idx = [res.best_index, 0, 1, B - 1]
