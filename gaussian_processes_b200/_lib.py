@@ -50,6 +50,7 @@ _PROTOS = {
     "gpb_trtri": (c_int, [vp, _i64, _i64, _i64, c_int, vp, _i64, _i64, vp, _i64, _i64, vp, _i64, _i64, vp]),
     "gpb_lauum": (c_int, [vp, _i64, _i64, _i64, c_int, vp, _i64, _i64, vp]),
     "gpb_tril": (c_int, [vp, _i64, _i64, vp]),
+    "gpb_tril_copy": (c_int, [vp, _i64, vp, _i64, _i64, vp]),
     "gpb_copy2d": (c_int, [vp, _i64, vp, _i64, _i64, _i64, vp]),
     "gpb_download_2d": (c_int, [vp, _i64, vp, _i64, _i64, _i64, c_int, vp]),
     "gpb_gemm_nt": (c_int, [vp, _i64, vp, _i64, vp, _i64, vp, _i64, _i64, _i64, _i64, c_double, c_double,

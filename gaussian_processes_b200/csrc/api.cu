@@ -442,6 +442,11 @@ int gpb_tril(double* A, int64_t n, int64_t ld, void* stream) {
     return gpb_launch_tril(A, n, ld, 0, 1, S(stream));
 }
 
+int gpb_tril_copy(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, void* stream) {
+    GPB_REQUIRE(dst && src && n >= 0 && ldd >= n && lds >= n, "bad argument");
+    return gpb_launch_tril_copy(dst, ldd, src, lds, n, S(stream));
+}
+
 int gpb_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
                void* stream) {
     return gpb_launch_copy2d(dst, ldd, src, lds, rows, cols, 0, 0, 1, S(stream));
@@ -623,7 +628,7 @@ int gpb_gp_eval_host(int kind, const double* thetas, int batch, const double* x,
 __global__ void stage_pack_kernel(const double* out3, const double* out16, const int* info, double* pack) {
     const int t = threadIdx.x;
     if (t < 3) pack[t] = out3[t];
-    else if (t < 19) pack[t] = out16[t - 3];
+    else if (t < 19) pack[t] = out16 ? out16[t - 3] : 0.0;      // null until the gradient stage has run
     else if (t == 19) pack[t] = (double)info[0];
     else if (t < GPB_STAGE_PACK) pack[t] = 0.0;
 }
@@ -700,7 +705,7 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
     done |= stages & 15u;
     if (host_out) {
         if (!packed) {
-            stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, w.out8, w.info, w.pack);
+            stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, (stages & 8u) ? w.out8 : nullptr, w.info, w.pack);
             GPB_LAUNCH_CHECK("stage_pack_kernel");
         }
         void* hp;

@@ -77,6 +77,7 @@ int gpb_launch_loglh(const double* L, long long n_valid, long long ld, long long
                      const double* y, long long sy, const double* alpha, long long svec,
                      const int* info, double* out3, cudaStream_t st);
 int gpb_launch_tril(double* A, long long n, long long ld, long long sA, int batch, cudaStream_t st);
+int gpb_launch_tril_copy(double* dst, long long ldd, const double* src, long long lds, long long n, cudaStream_t st);
 int gpb_launch_copy2d(double* dst, long long ldd, const double* src, long long lds, long long rows,
                       long long cols, long long sD, long long sS, int batch, cudaStream_t st);
 

@@ -677,6 +677,13 @@ __global__ void tril_kernel(double* A, long long n, long long ld, long long sA) 
     if (r < n && c < n && c > r) A[r * ld + c] = 0.0;
 }
 
+// dst = tril(src): the strict upper triangle of src is never read (the factorisation never writes it)
+__global__ void tril_copy_kernel(double* dst, long long ldd, const double* src, long long lds, long long n) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y; r < n; r += (long long)gridDim.y * blockDim.y)
+        if (c < n) dst[r * ldd + c] = (c <= r) ? src[r * lds + c] : 0.0;
+}
+
 __global__ void copy2d_kernel(double* dst, long long ldd, const double* src, long long lds,
                               long long rows, long long cols, long long sD, long long sS) {
     dst += (long long)blockIdx.z * sD;
@@ -966,6 +973,17 @@ int gpb_launch_tril(double* A, long long n, long long ld, long long sA, int batc
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 7) / 8), (unsigned)batch);
     tril_kernel<<<grid, block, 0, st>>>(A, n, ld, sA);
     GPB_LAUNCH_CHECK("tril_kernel");
+    return GPB_OK;
+}
+
+int gpb_launch_tril_copy(double* dst, long long ldd, const double* src, long long lds, long long n, cudaStream_t st) {
+    if (n == 0) return GPB_OK;
+    dim3 block(32, 8);
+    long long gy = (n + 7) / 8;
+    if (gy > 16384) gy = 16384;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)gy, 1);
+    tril_copy_kernel<<<grid, block, 0, st>>>(dst, ldd, src, lds, n);
+    GPB_LAUNCH_CHECK("tril_copy_kernel");
     return GPB_OK;
 }
 

@@ -179,8 +179,8 @@ class Engine(object):
 
     def Lxx_host(self):
         self.require_pd()
-        L = self._c["L"].clone()
-        call("gpb_tril", D.ptr(L), self.npad, self.npad, D.stream_ptr())
+        L = D.empty(self.n, self.n)          # tril(L): the never-written upper triangle is not read
+        call("gpb_tril_copy", D.ptr(L), self.n, D.ptr(self._c["L"]), self.npad, self.n, D.stream_ptr())
         return D.download_2d(L, self.n, self.n)
 
     def alpha(self):

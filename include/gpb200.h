@@ -97,6 +97,9 @@ int gpb_lauum(const double* V, int64_t n, int64_t ldv, int64_t stride_v, int bat
               int64_t ldk, int64_t stride_k, void* stream);
 /* zero the strict upper triangle (what scipy returns for Lxx).                          */
 int gpb_tril(double* A, int64_t n, int64_t ld, void* stream);
+/* dst = tril(src) without reading the strict upper triangle of src (which gpb_potrf never
+ * writes): how GP.Lxx (gp/gp.py:278-294) is extracted from the factorisation buffer.          */
+int gpb_tril_copy(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t n, void* stream);
 int gpb_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows,
                int64_t cols, void* stream);
 /* rows x cols block, device -> HOST.  dst_pinned != 0: the destination is page-locked, one
