@@ -404,6 +404,10 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const GradArgs a) {
 // slices are exactly the Jacobian slices in order, so the slice set is a compile-time constant
 // (no run-time picks), two adjacent columns per lane with 128-bit loads, and a register budget
 // that lets three CTAs share an SM.
+// ncu (B=8, N=4096): 46 us per candidate, FP64 pipe 34 % active, top stall long_scoreboard (latency of
+// the Ki / x / alpha loads at 24 warps per SM).  A four-columns-per-lane variant (six 128-bit loads in
+// flight, 114 registers, two CTAs per SM) was built and measured: -14 % at N=4096 (1.38 -> 1.18 ms per
+// 32 candidates, 0.3 % of the step) but +15 % at N=1024 where rows are short -- not kept.
 template <int KIND>
 __global__ void __launch_bounds__(256, 3) grad_jac_kernel(const GradArgs a) {
     constexpr int NP = (KIND == GPB_GAUSSIAN) ? 2 : 3;
