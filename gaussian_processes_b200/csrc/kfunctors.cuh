@@ -91,6 +91,9 @@ static __constant__ double gpb_exp_c[16] = {
     1.4426950408889634074, 6755399441055744.0};
 static __constant__ double gpb_exp_ln2[2] = {-6.93147180559945286227e-01, -2.31904681384629955842e-17};
 
+// (The same treatment of sincos for the periodic functor -- Cody-Waite + minimax kernels from a
+// constant table -- was built and measured: no change, N=8192 K-only build 0.297 ms either way; the
+// periodic element kernels already run ~50 FP64 operations per element at ~60 % of the FP64 pipe.)
 // W independent arguments at once: the Horner steps run coefficient-major, so each coefficient is
 // fetched once per W DFMAs (the element kernels evaluate 2-8 independent separations per thread).
 template <int W>
