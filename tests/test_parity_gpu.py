@@ -566,3 +566,31 @@ def test_symbolic_kernel_new_function_vs_lambdified():
     Ki = cho_solve(cf, np.eye(x.size))
     grad = [0.5 * al @ Ji @ al - 0.5 * np.sum(Ki * Ji) for Ji in J] + [s * (al @ al) - s * np.trace(Ki)]
     assert_parity(gp.log_lh, llh) and assert_parity(gp.dloglh_dtheta, np.array(grad))
+
+
+# ------------------------------------------------------------------ host-buffer posterior entry points
+def test_mean_pinned_and_pageable_paths(oracle):
+    """gpb_post_mean_host stages small test sets through a page-locked buffer and copies larger ones
+    (> 64 MB of staging) straight from / to pageable memory: both against the oracle on a subset."""
+    x, y = synth_xy(40, 2)
+    gp = GP(GaussianKernel(1.0, 0.6), x, y, s=0.5)
+    o = oracle.OracleGP(oracle.GAUSSIAN, (1.0, 0.6), x, y, 0.5)
+    rng = np.random.RandomState(0)
+    for m in (1, 33, 70000, 4300000):
+        xo = rng.uniform(-7, 7, m)
+        got = gp.mean(xo)
+        assert got.shape == (m,)
+        idx = rng.randint(0, m, size=min(m, 500))
+        assert_parity(got[idx], o.mean(xo[idx]), RTOL, "mean m=%d" % m)
+
+
+@pytest.mark.parametrize("m", [511, 512, 513])
+def test_cov_host_call_and_panel_path_agree(oracle, m):
+    """cov() is one gpb_post_cov_host call up to 512 test points and the pipelined panel path above."""
+    x, y = synth_xy(130, 6)
+    xo = np.linspace(-6.5, 6.5, m)
+    gp = GP(PeriodicKernel(1.1, 0.9, 1.6), x, y, s=0.6)
+    o = oracle.OracleGP(oracle.PERIODIC, (1.1, 0.9, 1.6), x, y, 0.6)
+    c = gp.cov(xo)
+    assert_parity(c, o.cov(xo), RTOL, "cov m=%d" % m)
+    assert np.array_equal(c, c.T)
