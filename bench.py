@@ -362,7 +362,7 @@ def run_ours(args):
         t_b = (time.perf_counter() - t0) / reps
         small = {"workload": "C1: N=50 GaussianKernel(1, 0.2), s=0: cold log_lh + dloglh_dtheta + mean + cov at 100 test points, one GP object",
                  "ms_per_bundle": t_b * 1e3, "bundles_per_s": 1.0 / t_b,
-                 "launches_per_bundle": "2 (evaluation) + 1 (mean) + 4 (cov)", "host_syncs_per_bundle": 3}
+                 "launches_per_bundle": "3 (build, factor+invert, tail) + 1 (mean) + 1 (cov)", "host_syncs_per_bundle": 3}
         if not args.no_cpu_baseline:
             oracle = load_oracle()
             impl = "ref" if oracle.have_ref() else "c"

@@ -92,6 +92,12 @@ int gpb_launch_small_tail(int kind, const KParams* P, const KParams* Pb, int bat
 // strictly upper / lower 32x32 sub-blocks) instead of a zero_diag_blocks launch.  pack (optional):
 // the 24-double read-back block of gpb_gp_stages for batch 1.
 
+// cov(xo) of a one-block GP (n <= 128) at m <= 128 test points in one launch, when
+// gpb_small_cov_smem(m, n) <= 200 KB
+size_t gpb_small_cov_smem(long long m, long long n);
+int gpb_launch_small_cov(int kind, const KParams* P, const double* xo, long long m, const double* x, long long n,
+                         const double* W, long long ldw, double* out, long long ldo, cudaStream_t st);
+
 // reduce.cu
 int gpb_launch_gemv(const double* A, long long rows, long long cols, long long lda, const double* x,
                     double* y, double alpha, double beta, cudaStream_t st);

@@ -243,7 +243,140 @@ __global__ void __launch_bounds__(256, 1) small_tail_kernel(const TailArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Posterior covariance of a one-block GP at up to 128 test points in ONE launch (gp/gp.py:599-625):
+//   Kx = K(xo, x) generated into shared memory, Z = Kx W^T (W = L^-1 read through L2),
+//   cov = K(xo, xo) - Z Z^T with K(xo, xo) generated in the epilogue (lower blocks + mirror).
+// The four-launch path (two builders, two TMA GEMMs) spends ~47 us of kernel latency on what is
+// 2 MFLOP of work at the reference's test-suite scale.
+// ---------------------------------------------------------------------------
+struct CovArgs {
+    KParams P;
+    const double* xo;       // [m] device
+    const double* x;        // [n] device
+    int m, n;
+    const double* W;        // [128 x 128] lower
+    long long ldw;
+    double* out;            // [m x m], row stride ldo
+    long long ldo;
+    int ldz;                // shared-memory row stride (= roundup(n, 32) + 4)
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 1) small_cov_kernel(const CovArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int m = a.m, n = a.n, LD = a.ldz;
+    const int nb = (n + TB - 1) / TB, nn = nb * TB;          // k / column blocks of Kx and Z
+    const int mb = (m + TB - 1) / TB, mm = mb * TB;          // row blocks
+    double* Kx = sm;                                         // [mm][LD]
+    double* Zs = sm + (size_t)mm * LD;                       // [mm][LD]
+    double* xs = Zs + (size_t)mm * LD;                       // x  (nn)
+    double* xos = xs + GPB_NB;                               // xo (mm)
+    __shared__ KParams sP;
+    if (tid == 0) sP = a.P;
+    if (tid < GPB_NB) {
+        xs[tid] = (tid < n) ? a.x[tid] : 0.0;
+        xos[tid] = (tid < m) ? a.xo[tid] : 0.0;
+    }
+    __syncthreads();
+    // ---- Kx[r][c] = k(xo_r - x_c), zero in the pad ----------------------------------------
+    for (int e = tid; e < mm * (nn / 2); e += 256) {
+        const int r = e / (nn / 2), c = (e % (nn / 2)) * 2;
+        double u[2][10];
+        const double dd[2] = {xos[r] - xs[c], xos[r] - xs[c + 1]};
+        gpb_eval_unique_v<KIND, 2>(sP, dd, 1u, u);
+        const bool vr = r < m;
+        Kx[r * LD + c] = (vr && c < n) ? u[0][0] : 0.0;
+        Kx[r * LD + c + 1] = (vr && c + 1 < n) ? u[1][0] : 0.0;
+    }
+    __syncthreads();
+    // ---- Z[rows of block bi][block bj] = sum_{kb <= bj} Kx[bi, kb] W[bj, kb]^T ----------------
+    for (int item = wid; item < mb * nb * 2; item += 8) {
+        const int hf = item & 1, blkid = item >> 1, bi = blkid / nb, bj = blkid % nb;
+        double acc[2][4][2];
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) acc[rt][ct][0] = acc[rt][ct][1] = 0.0;
+        for (int kb = 0; kb <= bj; kb++)
+            strip_mm_g(acc, Kx + bi * TB * LD + kb * TB, LD, 1,
+                       a.W + (long long)bj * TB * a.ldw + kb * TB, 1, (int)a.ldw, hf, g, t);
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) {
+                double* p = Zs + (bi * TB + hf * 16 + rt * 8 + g) * LD + bj * TB + ct * 8 + 2 * t;
+                p[0] = acc[rt][ct][0];
+                p[1] = acc[rt][ct][1];
+            }
+    }
+    __syncthreads();
+    // ---- cov[bi, bj] = K(xo, xo) - Z[bi] Z[bj]^T for bj <= bi, mirrored ----------------------
+    const int npair = mb * (mb + 1) / 2;
+    for (int item = wid; item < npair * 2; item += 8) {
+        const int pr = item >> 1, hf = item & 1;
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= pr) bi++;
+        const int bj = pr - bi * (bi + 1) / 2;
+        double acc[2][4][2];
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) acc[rt][ct][0] = acc[rt][ct][1] = 0.0;
+        for (int kb = 0; kb < nb; kb++)
+            strip_mm_g(acc, Zs + bi * TB * LD + kb * TB, LD, 1, Zs + bj * TB * LD + kb * TB, 1, LD, hf, g, t);
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) {
+                const int r = bi * TB + hf * 16 + rt * 8 + g, c = bj * TB + ct * 8 + 2 * t;
+                if (r >= m) continue;
+                double u[2][10];
+                const double dd[2] = {xos[r] - xos[c], xos[r] - xos[c + 1]};
+                gpb_eval_unique_v<KIND, 2>(sP, dd, 1u, u);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int cc = c + e;
+                    if (cc >= m || cc > r) continue;          // lower triangle; the mirror makes it exactly symmetric
+                    const double v = u[e][0] - acc[rt][ct][e];
+                    a.out[(long long)r * a.ldo + cc] = v;
+                    if (cc != r) a.out[(long long)cc * a.ldo + r] = v;
+                }
+            }
+    }
+}
+
 }  // namespace
+
+size_t gpb_small_cov_smem(long long m, long long n) {
+    const long long mm = (m + TB - 1) / TB * TB, ldz = (n + TB - 1) / TB * TB + 4;
+    return (size_t)(2 * mm * ldz + 2 * GPB_NB) * 8;
+}
+
+// cov(xo) of a one-block GP in one launch; returns GPB_ERR_ARG (without setting an error text the
+// caller would show) when the problem does not fit the shared-memory budget -> use the GEMM path.
+int gpb_launch_small_cov(int kind, const KParams* P, const double* xo, long long m, const double* x, long long n,
+                         const double* W, long long ldw, double* out, long long ldo, cudaStream_t st) {
+    GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(m >= 1 && m <= GPB_NB && n >= 1 && n <= GPB_NB && P && xo && x && W && out, "bad argument");
+    const size_t smem = gpb_small_cov_smem(m, n);
+    GPB_REQUIRE(smem <= (size_t)200 * 1024, "problem too large for the one-launch covariance");
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CUDA(cudaFuncSetAttribute(small_cov_kernel<GPB_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        GPB_CUDA(cudaFuncSetAttribute(small_cov_kernel<GPB_PERIODIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    CovArgs a;
+    a.P = *P; a.xo = xo; a.x = x; a.m = (int)m; a.n = (int)n; a.W = W; a.ldw = ldw; a.out = out; a.ldo = ldo;
+    a.ldz = (int)((n + TB - 1) / TB * TB + 4);
+    GpbProfScope prof(GPB_KC_GEMM, st);
+    if (kind == GPB_GAUSSIAN) small_cov_kernel<GPB_GAUSSIAN><<<1, 256, smem, st>>>(a);
+    else small_cov_kernel<GPB_PERIODIC><<<1, 256, smem, st>>>(a);
+    GPB_LAUNCH_CHECK("small_cov_kernel");
+    return GPB_OK;
+}
 
 // One CTA per GP: alpha, log_lh and (when Ki != nullptr) K^-1 + the gradient brackets.
 // W must hold the complete L^-1 of a single 128-block (potrf with n == 128).

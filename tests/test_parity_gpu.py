@@ -143,7 +143,13 @@ def test_one_block_gp_vs_oracle(oracle, n, kparams, s):
     for key in ("log_lh", "inv_Kxx_y", "inv_Kxx", "Lxx", "dlh_dtheta"):
         assert_parity(getattr(gp, key), getattr(o, key), RTOL, key)
     assert_parity(gp.mean(xo), o.mean(xo), RTOL, "mean")
-    assert_parity(gp.cov(xo), o.cov(xo), RTOL, "cov")
+    c37 = gp.cov(xo)                                   # one-launch covariance (small.cu)
+    assert_parity(c37, o.cov(xo), RTOL, "cov") and np.array_equal(c37, c37.T)
+    for m2 in (1, 32, 100, 128, 129):                  # every row-block count, and past the one-launch limit
+        xo2 = np.linspace(-5.5, 6.1, m2)
+        c2 = gp.cov(xo2)
+        assert_parity(c2, o.cov(xo2), RTOL, "cov m=%d" % m2)
+        assert np.array_equal(c2, c2.T)
     assert_parity(gp.var(xo), np.diag(o.cov(xo)), RTOL, "var")
     assert_parity(gp.dm_dtheta(xo), o.dm_dtheta(xo), RTOL, "dm")
     assert_parity(gp.d2loglh_normalised(), o.d2lh_dtheta2_with(1.0, o.dloglh_dtheta), RTOL, "d2lh(lh=1)")
