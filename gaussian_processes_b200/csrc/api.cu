@@ -658,6 +658,15 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
     int stt;
     unsigned done = 0;
     bool packed = false;
+    // the read-back block is written by the last kernel straight into page-locked host memory
+    // (device-addressable under unified addressing): no copy-engine round trip after the chain
+    double* pack_dst = w.pack;
+    if (host_out) {
+        void* hp;
+        stt = post_pin_reserve(GPB_STAGE_PACK * 8, &hp);
+        if (stt) return stt;
+        pack_dst = (double*)hp;
+    }
     if (np_ == GPB_NB) {
         // a GP that fits one 128-block: build, factor + invert (one CTA), then everything else in
         // one more launch -- all four stages at once, whatever subset was asked for
@@ -669,7 +678,7 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
             stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n, false);
             if (stt) return stt;
             stt = gpb_launch_small_tail(kind, &P, nullptr, 1, x, n, ypad, 0, w.L, np_, 0, w.W, np_, 0, w.Ki, np_, 0,
-                                        w.z, w.alpha, np_, w.info, w.out3, w.out8, w.W, w.V, np_, 0, w.pack, st);
+                                        w.z, w.alpha, np_, w.info, w.out3, w.out8, w.W, w.V, np_, 0, pack_dst, st);
             if (stt) return stt;
             done = 15u;
             packed = true;
@@ -705,15 +714,11 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
     done |= stages & 15u;
     if (host_out) {
         if (!packed) {
-            stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, (stages & 8u) ? w.out8 : nullptr, w.info, w.pack);
+            stage_pack_kernel<<<1, 32, 0, st>>>(w.out3, (stages & 8u) ? w.out8 : nullptr, w.info, pack_dst);
             GPB_LAUNCH_CHECK("stage_pack_kernel");
         }
-        void* hp;
-        stt = post_pin_reserve(GPB_STAGE_PACK * 8, &hp);
-        if (stt) return stt;
-        GPB_CUDA(cudaMemcpyAsync(hp, w.pack, GPB_STAGE_PACK * 8, cudaMemcpyDeviceToHost, st));
         GPB_CUDA(cudaStreamSynchronize(st));
-        memcpy(host_out, hp, GPB_STAGE_PACK * 8);
+        memcpy(host_out, pack_dst, GPB_STAGE_PACK * 8);
         host_out[20] = (double)done;       // stages this call completed (a one-block GP completes all four)
     }
     return GPB_OK;
