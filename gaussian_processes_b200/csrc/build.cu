@@ -466,8 +466,9 @@ __global__ void __launch_bounds__(256, 3) grad_jac_kernel(const GradArgs a) {
     double* out = a.partial + ((long long)blockIdx.z * gridDim.x + blockIdx.x) * GPB_RED_WIDTH;
 #pragma unroll
     for (int q = 0; q < GPB_RED_MAXS; q++) {
-        const double s0 = block_sum(q < NP ? t0[q < NP ? q : 0] : 0.0, red);
-        const double s1 = block_sum(q < NP ? t1[q < NP ? q : 0] : 0.0, red);
+        // only the NP live slots are reduced (each block_sum is two barriers + two shuffle trees)
+        const double s0 = (q < NP) ? block_sum(t0[q < NP ? q : 0], red) : 0.0;
+        const double s1 = (q < NP) ? block_sum(t1[q < NP ? q : 0], red) : 0.0;
         if (threadIdx.x == 0) { out[q] = s0; out[GPB_RED_MAXS + q] = s1; }
     }
     {
@@ -490,7 +491,9 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const double* partial
 }
 
 int gpb_grad_reduce_blocks(long long n) {
-    long long nb = (n + 7) / 8;
+    // four rows per warp (strided, so the triangular row lengths balance): with one row per warp the
+    // block-wide reduction at the end of every CTA cost as much as its 8 rows at N = 1024
+    long long nb = (n + 31) / 32;
     if (nb > 148 * 4) nb = 148 * 4;
     if (nb < 1) nb = 1;
     return (int)nb;
