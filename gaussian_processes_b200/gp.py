@@ -319,6 +319,15 @@ class GP(object):
             return self._nan(nth, nth)
         return self._d2lh(1.0, self.dloglh_dtheta)
 
+    def d2loglh_dtheta2(self):
+        r"""Hessian of the marginal **log** likelihood w.r.t. ``params``,
+        :math:`\partial^2 \log p / \partial\theta_i\partial\theta_j = (\partial^2 p)/p - (\partial_i p)(\partial_j p)/p^2`,
+        assembled from the likelihood-normalised second derivative and ``dloglh_dtheta`` -- what a
+        Newton step on the hyperparameters needs, finite at sizes where ``lh`` itself underflows
+        (additive API; SURVEY 8f #3)."""
+        g = self.dloglh_dtheta
+        return self.d2loglh_normalised() - np.outer(g, g)
+
     # ------------------------------------------------------------------ posterior (gp.py:504-662)
     def Kxoxo(self, xo):
         r"""Kernel covariance matrix of new sample locations (:math:`m\times m`)."""

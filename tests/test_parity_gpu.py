@@ -600,3 +600,25 @@ def test_cov_host_call_and_panel_path_agree(oracle, m):
     c = gp.cov(xo)
     assert_parity(c, o.cov(xo), RTOL, "cov m=%d" % m)
     assert np.array_equal(c, c.T)
+
+
+def test_log_likelihood_hessian_vs_finite_differences():
+    """d2loglh_dtheta2 (additive API) against central differences of dloglh_dtheta, at a size where
+    lh underflows to 0 and the reference's d2lh_dtheta2 is identically zero."""
+    x, y = synth_xy(1500, 8)
+    th0 = np.array([1.1, 0.45, 0.9])
+    gp = GP(GaussianKernel(*th0[:2]), x, y, s=th0[2])
+    assert gp.lh == 0 and not np.any(gp.d2lh_dtheta2)
+    H = gp.d2loglh_dtheta2()
+    assert np.allclose(H, H.T, rtol=1e-9, atol=1e-6 * np.abs(H).max())
+    eps = 1e-5
+    for j in range(3):
+        tp, tm = th0.copy(), th0.copy()
+        tp[j] += eps
+        tm[j] -= eps
+        gp.params = tp
+        gpl = gp.dloglh_dtheta.copy()
+        gp.params = tm
+        gmi = gp.dloglh_dtheta.copy()
+        fd = (gpl - gmi) / (2 * eps)
+        assert np.allclose(H[:, j], fd, rtol=2e-5, atol=2e-5 * np.abs(H).max()), (j, H[:, j], fd)
