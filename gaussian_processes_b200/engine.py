@@ -117,7 +117,8 @@ class Engine(object):
         non-finite data (scipy check_finite, gp.py:294), LinAlgError when Kxx is not PD."""
         if not self.finite:
             raise ValueError("array must not contain infs or NaNs")
-        self._run(stages)
+        if self._c.get("info", 0) == 0:         # a failed factorisation is not inverted
+            self._run(stages)
         info = self._c["info"]
         if info != 0:
             raise np.linalg.LinAlgError(
