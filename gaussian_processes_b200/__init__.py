@@ -16,9 +16,10 @@ from . import ext
 from .gp import GP
 from .kernels import Kernel, PeriodicKernel, GaussianKernel, SymbolicKernel
 from .mlii import fit_MLII, MLIIResult
+from .posterior import sharded_posterior
 
 __all__ = ["ext", "GP", "Kernel", "PeriodicKernel", "GaussianKernel", "SymbolicKernel", "fit_MLII", "MLIIResult",
-           "install_as_gp"]
+           "sharded_posterior", "install_as_gp"]
 __version__ = "0.1.0"
 
 
