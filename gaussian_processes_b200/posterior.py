@@ -38,7 +38,14 @@ def sharded_posterior(gp, xo, want_cov=True, gather_cov=False, group=None, distr
         return mean, cov, (0, m)
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    bounds = [shard_bounds(m, world, r) for r in range(world)]
+    # shards start on multiples of 128 test points (the tile edge) whenever there are enough of them,
+    # so that a shard's own diagonal block of the covariance takes the symmetric tile path of cov_rows
+    unit = 128 if m >= 128 * world else 1
+    nblk = (m + unit - 1) // unit
+    bounds = []
+    for r in range(world):
+        b0, b1 = shard_bounds(nblk, world, r)
+        bounds.append((min(m, b0 * unit), min(m, b1 * unit)))
     counts = [b[1] - b[0] for b in bounds]
     lo, hi = bounds[rank]
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
