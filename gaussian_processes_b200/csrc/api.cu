@@ -731,7 +731,7 @@ int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(m >= 0 && n >= 1 && theta && x && alpha, "bad argument");
     if (m == 0) return GPB_OK;
-    GPB_REQUIRE(xo_host && scratch && out_host, "null pointer");
+    GPB_REQUIRE(xo_host && out_host && (scratch || m <= 2048), "null pointer");
     cudaStream_t st = S(stream);
     const long long mr = roundup(m, 32);
     KParams P;
@@ -777,7 +777,11 @@ int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int
 // enough that pipelining its download does not pay (gp.py:599-625):
 //   cov = K(xo,xo) - Z Z^T,  Z = K(xo,x) L^-T  (W = L^-1 from gpb_trtri / gpb_gp_stages).
 // scratch: DEVICE, >= gpb_post_cov_scratch_doubles(m, n) doubles, 256-byte aligned.
+static bool post_cov_one_launch(int64_t m, int64_t n) {
+    return roundup(n, GPB_NB) == GPB_NB && m >= 1 && m <= GPB_NB && gpb_small_cov_smem(m, n) <= (size_t)200 * 1024;
+}
 size_t gpb_post_cov_scratch_doubles(int64_t m, int64_t n) {
+    if (post_cov_one_launch(m, n)) return 0;       // one-block GP, one block of test points: no device scratch
     const size_t mp = (size_t)roundup(m, GPB_NB), np_ = (size_t)roundup(n, GPB_NB);
     return mp + 2 * mp * np_ + mp * mp;
 }
@@ -787,7 +791,7 @@ int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int6
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(m >= 0 && n >= 1 && theta && x && W, "bad argument");
     if (m == 0) return GPB_OK;
-    GPB_REQUIRE(xo_host && scratch && out_host && ld_out >= m, "bad argument");
+    GPB_REQUIRE(xo_host && out_host && ld_out >= m && (scratch || post_cov_one_launch(m, n)), "bad argument");
     GPB_REQUIRE((uintptr_t)scratch % 256 == 0, "scratch must be 256-byte aligned");
     cudaStream_t st = S(stream);
     const long long mp = roundup(m, GPB_NB), np_ = roundup(n, GPB_NB);
@@ -797,7 +801,7 @@ int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int6
     double* C = Z + mp * np_;
     KParams P;
     gpb_make_kparams(&P, kind, theta, 0.0);
-    if (np_ == GPB_NB && m <= GPB_NB && gpb_small_cov_smem(m, n) <= (size_t)200 * 1024) {
+    if (post_cov_one_launch(m, n)) {
         // one-block GP, one block of test points: the whole covariance in a single launch that reads
         // xo from and writes the m x m result to page-locked host memory directly (<= 128 KB)
         void* hp;

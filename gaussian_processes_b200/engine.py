@@ -338,7 +338,9 @@ class Engine(object):
         m = int(xo.size)
         out = np.empty(m, dtype=DTYPE)
         if m:
-            scratch = D.empty(2 * D.roundup(m, 32))
+            # up to 2048 points the library reads xo / writes the means in page-locked host memory and
+            # needs no device scratch
+            scratch = D.empty(2 * D.roundup(m, 32)) if m > 2048 else None
             call("gpb_post_mean_host", self.kind, self._theta(), xo.ctypes.data, m, D.ptr(self.dx), self.n,
                  D.ptr(a), D.ptr(scratch), out.ctypes.data, D.stream_ptr())
         return out
@@ -388,7 +390,8 @@ class Engine(object):
             # small result: the four launches and both copies in one library call
             xo = np.ascontiguousarray(xo, dtype=DTYPE).reshape(-1)
             out = np.empty((m, m), dtype=DTYPE)
-            scratch = D.empty(int(_lib.lib.gpb_post_cov_scratch_doubles(m, self.n)))
+            nscr = int(_lib.lib.gpb_post_cov_scratch_doubles(m, self.n))      # 0: the one-launch path
+            scratch = D.empty(nscr) if nscr else None
             call("gpb_post_cov_host", self.kind, self._theta(), xo.ctypes.data, m, D.ptr(self.dx), self.n,
                  D.ptr(W), self.npad, D.ptr(scratch), out.ctypes.data, m, D.stream_ptr())
             return out

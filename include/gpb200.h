@@ -179,13 +179,15 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
                   void* stream);
 /* Posterior mean K(xo, x) alpha (gp.py:574-597) with HOST xo / out: upload, fused
  * kernel-times-vector (K(xo, x) is never materialised), download, synchronise.
- * scratch: DEVICE, >= 2 * roundup(m, 32) doubles.                                           */
+ * scratch: DEVICE, >= 2 * roundup(m, 32) doubles; may be NULL for m <= 2048 (the kernel then reads
+ * xo and writes the result in page-locked host memory directly, no copy engine involved).      */
 int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int64_t m,
                        const double* x, int64_t n, const double* alpha, double* scratch,
                        double* out_host, void* stream);
 /* Posterior covariance (gp.py:599-625) with HOST xo / out for small test sets:
  * K(xo,xo) - Z Z^T, Z = K(xo,x) L^-T, W = L^-1 [roundup(n,128)]^2 (stage 2 above).
- * scratch: DEVICE, 256-byte aligned, >= gpb_post_cov_scratch_doubles(m, n) doubles.           */
+ * scratch: DEVICE, 256-byte aligned, >= gpb_post_cov_scratch_doubles(m, n) doubles; that is 0
+ * (scratch may be NULL) for a GP of n <= 128 at m <= 128 test points, which is one launch.      */
 size_t gpb_post_cov_scratch_doubles(int64_t m, int64_t n);
 int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int64_t m,
                       const double* x, int64_t n, const double* W, int64_t ldw, double* scratch,
