@@ -26,6 +26,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every worker; the reference arm is a CPU
+    # measurement and must use the host's cores whatever launched it (read before numpy loads OpenBLAS)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -106,11 +112,25 @@ def load_oracle():
 
 
 def blas_threads():
+    """Threads the BLAS pools behind numpy / scipy actually use (reported as cpu_baseline.cores)."""
     try:
         from threadpoolctl import threadpool_info
         return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
         return os.cpu_count() or 1
+
+
+def use_all_host_cores():
+    """Size every BLAS / OpenMP pool to the box's cores (an inherited OMP_NUM_THREADS=1 -- torchrun sets
+    it -- would otherwise time the reference on one thread).  Returns the thread count in effect."""
+    import scipy.linalg  # noqa: F401  (loads scipy's own OpenBLAS so the limit reaches it too)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncpu)
+    except Exception:
+        pass
+    return blas_threads()
 
 
 def cpu_eval_once(oracle, impl, x, y, theta):
@@ -127,6 +147,7 @@ def run_reference(args):
         return
     oracle = load_oracle()
     impl = "ref" if oracle.have_ref() else "c"
+    cores = use_all_host_cores()
     x, y = synth_xy(args.n, 0)
     th = candidates(0, 0, max(args.steps + args.warmup, 1))
     for w in range(args.warmup):
@@ -136,7 +157,6 @@ def run_reference(args):
         cpu_eval_once(oracle, impl, x, y, th[args.warmup + k])
     dt = time.perf_counter() - t0
     value = args.steps / dt
-    cores = blas_threads()
     sample = "1 candidate (one cold-cache log_lh + dloglh_dtheta at N=%d) per step" % args.n
     line = {
         "impl": "reference", "metric": "log_lh+dloglh_dtheta evals/sec at N=%d fp64" % args.n,
@@ -300,6 +320,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             oracle = load_oracle()
             impl = "ref" if oracle.have_ref() else "c"
+            use_all_host_cores()
             th = candidates(0, 0, 3)
             cpu_eval_once(oracle, impl, x, y, th[0])
             t0 = time.perf_counter()

@@ -8,8 +8,17 @@
 #include "kfunctors.cuh"
 #include "launch.h"
 
+#include <mutex>
 long long g_gpb_launches = 0;
 static thread_local char g_err[512] = "";
+
+// The library keeps process-global staging state (pinned rings and slots, the device pool, the fork/join
+// events of the candidate groups, profiling lists).  ctypes drops the GIL during a call, so two host
+// threads can be inside the library at once: every entry point that touches that state holds this lock
+// for its duration (recursive: the host-buffer entry points call the device-pointer ones).  Entry points
+// that only enqueue kernels on the caller's stream do not take it.
+static std::recursive_mutex g_api_mu;
+#define GPB_API_LOCK std::lock_guard<std::recursive_mutex> gpb_api_guard(g_api_mu)
 
 void gpb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -358,17 +367,20 @@ double gpb_min_log(void) { return GPB_MIN_LOG; }
 int64_t gpb_launch_count(void) { return g_gpb_launches; }
 
 void gpb_profile_enable(int on) {
+    GPB_API_LOCK;
     prof_collect();
     g_gpb_profile = on;
     if (on) for (int c = 0; c < GPB_KC_COUNT; c++) { g_prof_ms[c] = 0.0; g_prof_n[c] = 0; }
 }
 int gpb_set_option(const char* name, int value) {
+    GPB_API_LOCK;
     for (auto& o : g_options)
         if (strcmp(o.name, name) == 0) { o.value = value; o.env_read = true; return GPB_OK; }
     gpb_set_error("gpb_set_option: unknown option %s", name);
     return GPB_ERR_ARG;
 }
 int gpb_profile_read(int cls, double* ms, int64_t* launches) {
+    GPB_API_LOCK;
     GPB_REQUIRE(cls >= 0 && cls < GPB_KC_COUNT, "bad kernel class");
     prof_collect();
     *ms = g_prof_ms[cls];
@@ -454,6 +466,7 @@ int gpb_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t
 
 int gpb_download_2d(double* dst_host, int64_t ld_host, const double* src_dev, int64_t ld_dev,
                     int64_t rows, int64_t cols, int dst_pinned, void* stream) {
+    GPB_API_LOCK;
     GPB_REQUIRE(rows >= 0 && cols >= 0 && ld_host >= cols && ld_dev >= cols, "bad extents");
     if (rows == 0 || cols == 0) return GPB_OK;
     GPB_REQUIRE(dst_host && src_dev, "null pointer");
@@ -572,6 +585,7 @@ static int eval_group(int kind, const double* thetas, int batch, const double* x
 
 int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, const double* y, int64_t n,
                 int want_grad, void* workspace, size_t workspace_bytes, double* result, void* stream) {
+    GPB_API_LOCK;
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(batch >= 1 && n >= 1 && thetas && x && y && workspace && result, "bad argument");
     GPB_REQUIRE(gpb_eval_workspace_bytes(n, batch, want_grad) <= workspace_bytes, "workspace too small (see gpb_eval_workspace_bytes)");
@@ -602,6 +616,7 @@ int gpb_gp_eval(int kind, const double* thetas, int batch, const double* x, cons
 
 int gpb_gp_eval_host(int kind, const double* thetas, int batch, const double* x, const double* y,
                      int64_t n, int want_grad, double* result) {
+    GPB_API_LOCK;
     GPB_REQUIRE(batch >= 1 && n >= 1 && thetas && x && y && result, "bad argument");
     const size_t wsb = gpb_eval_workspace_bytes(n, batch, want_grad);
     const size_t extra = (size_t)(2 * n + 8 * (size_t)batch) * 8 + 1024;
@@ -645,6 +660,7 @@ int gpb_eval_layout(int64_t n, int64_t* off, int noff) {
 
 int gpb_gp_stages(int kind, const double* theta, const double* x, const double* ypad, int64_t n,
                   unsigned stages, void* workspace, size_t workspace_bytes, double* host_out, void* stream) {
+    GPB_API_LOCK;
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(n >= 1 && theta && x && ypad && workspace, "bad argument");
     GPB_REQUIRE((uintptr_t)workspace % 256 == 0, "workspace must be 256-byte aligned");
@@ -728,6 +744,7 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
 // materialised (gp.py:574-597).  scratch: DEVICE, >= 2 * roundup(m, 32) doubles.
 int gpb_post_mean_host(int kind, const double* theta, const double* xo_host, int64_t m, const double* x,
                        int64_t n, const double* alpha, double* scratch, double* out_host, void* stream) {
+    GPB_API_LOCK;
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(m >= 0 && n >= 1 && theta && x && alpha, "bad argument");
     if (m == 0) return GPB_OK;
@@ -788,6 +805,7 @@ size_t gpb_post_cov_scratch_doubles(int64_t m, int64_t n) {
 int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int64_t m, const double* x,
                       int64_t n, const double* W, int64_t ldw, double* scratch, double* out_host,
                       int64_t ld_out, void* stream) {
+    GPB_API_LOCK;
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(m >= 0 && n >= 1 && theta && x && W, "bad argument");
     if (m == 0) return GPB_OK;
@@ -850,6 +868,7 @@ int gpb_post_cov_host(int kind, const double* theta, const double* xo_host, int6
 // ---- host-buffer drop-ins for the Cython signatures --------------------------------
 int gpb_kernel_slices_host(int kind, unsigned slice_mask, double* out, const double* x1, int64_t n1,
                            const double* x2, int64_t n2, const double* theta) {
+    GPB_API_LOCK;
     GPB_REQUIRE(kind == GPB_GAUSSIAN || kind == GPB_PERIODIC, "unknown kernel kind");
     GPB_REQUIRE(out && x1 && x2 && theta && n1 >= 0 && n2 >= 0, "bad argument");
     if (n1 == 0 || n2 == 0) return GPB_OK;

@@ -23,6 +23,25 @@ EPS = np.finfo(DTYPE).eps
 MIN = np.log(np.exp2(DTYPE(np.finfo(DTYPE).minexp + 4)))      # gp.py:17
 
 
+def fused_kind(kernel):
+    """``KIND`` of the fused CUDA functor that evaluates ``kernel``, or None.  A subclass of a
+    built-in kernel inherits ``KIND`` but may override ``K`` / ``jacobian`` / ``hessian`` (the
+    reference's GP calls exactly these methods, gp.py:264,271,276): the fused functor is only
+    taken when the element formulas are the built-in ones."""
+    from .kernels import GaussianKernel, PeriodicKernel
+    cls = type(kernel)
+    kind = getattr(cls, "KIND", None)
+    if kind is None:
+        return None
+    for base in (GaussianKernel, PeriodicKernel):
+        if isinstance(kernel, base):
+            for name in ("K", "__call__", "jacobian", "hessian", "_build", "_ext"):
+                if getattr(cls, name, None) is not getattr(base, name, None):
+                    return None
+            return kind
+    return None
+
+
 class memoprop(object):
     """Property whose value is computed once and kept in ``obj._memoized[name]``;
     ``del obj.name`` forgets it (semantics of gp.py:20-41)."""
@@ -72,6 +91,7 @@ class GP(object):
         self._s = None
         self._memoized = {}
         self._dev = None
+        self._data_gen = 0
         self.x = x
         self.y = y
         self.s = s
@@ -84,6 +104,7 @@ class GP(object):
         for k in self._STATE:
             setattr(self, k, state[k])
         self._dev = None
+        self._data_gen = 0
 
     def __copy__(self):
         new = type(self).__new__(type(self))
@@ -105,6 +126,9 @@ class GP(object):
         self._memoized = {}
         if data:
             self._dev = None
+            # generation of the observations: device-side copies (the batched evaluator's x / y) are
+            # keyed on it -- object identities are recycled by the allocator and cannot be
+            self._data_gen = getattr(self, "_data_gen", 0) + 1
 
     # ------------------------------------------------------------------ inputs (gp.py:129-240)
     @property
@@ -178,7 +202,7 @@ class GP(object):
         kernels have fused CUDA functors (``KIND``); any other ``Kernel`` subclass evaluates its
         matrices in its own Python methods and everything after that runs on the device."""
         kp = tuple(float(v) for v in self.K.params)
-        kind = getattr(type(self.K), "KIND", None)
+        kind = fused_kind(self.K)
         if kind is None:
             key = (("host", id(self.K)), kp, float(self._s))
             if self._dev is None or self._dev[0][0] != key[0]:

@@ -24,6 +24,8 @@ class MLIIResult(object):
     """Outcome of a batched search."""
 
     def __init__(self, best_index, candidates, log_lh, dloglh, refined=None):
+        #: index of the winning candidate; -1 when NO candidate has a finite log likelihood (every
+        #: Kxx non-PD or below the MIN clamp): the search found nothing and the GP is left untouched
         self.best_index = int(best_index)
         self.candidates = candidates
         self.log_lh = log_lh
@@ -33,13 +35,22 @@ class MLIIResult(object):
         self.refined = refined
 
     @property
+    def found(self):
+        """False when every candidate evaluated to -inf / NaN."""
+        return self.best_index >= 0
+
+    @property
     def best_params(self):
+        if not self.found:
+            return None
         if self.refined is not None:
             return self.refined["params"][self.refined["best"]].copy()
         return self.candidates[self.best_index].copy()
 
     @property
     def best_log_lh(self):
+        if not self.found:
+            return -np.inf
         if self.refined is not None:
             return self.refined["log_lh"][self.refined["best"]]
         return self.log_lh[self.best_index]
@@ -58,12 +69,26 @@ def select_best(log_lh):
     return int(np.argmax(key))
 
 
+def validate_candidates(cand, names=None):
+    """The checks ``Kernel.set_param`` / the ``s`` setter apply to one parameter vector
+    (gaussian.py:63-73, periodic.py:67-83, gp.py:192-193), applied to every row up front: a search must
+    not end on a winner the GP then refuses.  Kernel parameters must be >= EPS, s >= 0, all finite."""
+    eps = np.finfo(np.float64).eps
+    bad = ~np.isfinite(cand).all(axis=1) | (cand[:, :-1] < eps).any(axis=1) | (cand[:, -1] < 0)
+    if bad.any():
+        b = int(np.nonzero(bad)[0][0])
+        raise ValueError("invalid candidate %d: %s (kernel parameters must be >= EPS, s >= 0)" % (b, cand[b]))
+
+
 def _evaluator(gp):
     """One evaluator (device buffers + workspace) per GP object; new x / y arrays of the
     same length are re-uploaded into it instead of rebuilding it."""
+    from .gp import fused_kind
     ev = getattr(gp, "_batch_ev", None)
-    shape_key = (type(gp.K).KIND, gp._x.size)
-    data_key = (id(gp._x), id(gp._y))
+    shape_key = (fused_kind(gp.K), gp._x.size)
+    # generation counter bumped by every x / y assignment (GP._reset(data=True)); id() of the arrays
+    # is NOT a key: CPython hands a freed array's id to the next allocation
+    data_key = gp._data_gen
     if ev is None or ev[0] != shape_key:
         ev = [shape_key, data_key, _engine.BatchEvaluator(shape_key[0], gp._x, gp._y)]
         gp._batch_ev = ev
@@ -77,7 +102,8 @@ def batch_eval(gp, thetas, grad=True):
     thetas = np.ascontiguousarray(thetas, dtype=np.float64)
     if thetas.ndim != 2 or thetas.shape[1] != gp.params.size:
         raise ValueError("thetas must have shape [B, %d]" % gp.params.size)
-    if getattr(type(gp.K), "KIND", None) is None:
+    from .gp import fused_kind
+    if fused_kind(gp.K) is None:
         # user-defined kernel: its matrices come from Python methods, so candidates are evaluated one
         # by one through the GP properties (the linear algebra of each still runs on the device)
         trial = gp.copy()
@@ -198,11 +224,17 @@ def fit_MLII(gp, candidates, distributed=None, group=None, set_params=True, eval
     """
     import torch
     cand = np.ascontiguousarray(candidates, dtype=np.float64)
+    if cand.ndim != 2 or cand.shape[1] != gp.params.size:
+        raise ValueError("candidates must have shape [B, %d]" % gp.params.size)
     B, nth = cand.shape
+    if B == 0:
+        raise ValueError("fit_MLII needs at least one candidate")
+    validate_candidates(cand)
     if distributed is None:
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized()
-    if evaluate is None and getattr(type(gp.K), "KIND", None) is None:
+    from .gp import fused_kind
+    if evaluate is None and fused_kind(gp.K) is None:
         def evaluate(th):                       # user-defined kernel: per-candidate GP properties
             l, g = batch_eval(gp, th)
             bad = (~np.isfinite(l)).astype(np.float64)
@@ -234,6 +266,9 @@ def fit_MLII(gp, candidates, distributed=None, group=None, set_params=True, eval
     table = table.detach().cpu().numpy()
     llh, grad = table[:, 0].copy(), table[:, 1:1 + nth].copy()
     best = select_best(llh)
+    if not np.isfinite(llh[best]):
+        # nothing to pick: every Kxx was non-PD or under the MIN clamp.  The GP keeps its parameters.
+        return MLIIResult(-1, cand, llh, grad, None)
     refined = None
     if refine_top and refine_top > 0:
         order = np.argsort(-np.where(np.isnan(llh), -np.inf, llh), kind="stable")

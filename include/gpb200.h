@@ -20,7 +20,11 @@
  *     failure is NOT an error code: it is reported through the device `info` word
  *     (LAPACK convention: index+1 of the first non-positive pivot), which the Python
  *     layer turns into numpy.linalg.LinAlgError exactly where gp/gp.py:294 raises.
- *   - not thread-safe per handle-less call: one host thread per stream.
+ *   - threading: entry points that use the library's process-global staging state (every
+ *     *_host entry point, gpb_gp_eval, gpb_gp_stages, gpb_download_2d, options, profiling)
+ *     serialise on one internal lock, so concurrent host threads are safe (and do not
+ *     overlap inside those calls).  The stream-only entry points (gpb_kernel_build,
+ *     gpb_potrf, gpb_gemm_nt, ...) take no lock; use one host thread per stream for them.
  */
 #ifndef GPB200_H
 #define GPB200_H

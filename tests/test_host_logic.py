@@ -223,3 +223,70 @@ def test_symbolic_kernel_codegen_compiles_for_sm100a():
         SymbolicKernel(h * sym.Symbol("zz") * d, ("h",), (1.0,))          # unknown symbol
     with pytest.raises(ValueError):
         rq.set_param("w", 0.0)                                             # same validation as the built-ins
+
+
+# ------------------------------------------------------------------ round-2 host-logic fixes
+def test_data_generation_counter_not_object_identity():
+    """The batched evaluator re-uploads x / y when the GP's data generation moved.  Object ids cannot be
+    the key: CPython recycles them (assign gp.y twice and the third array usually gets the first one's id)."""
+    x, y = make_xy()
+    gp = GP(GaussianKernel(1, 1), x, y, s=1)
+    g0 = gp._data_gen
+    ids = {id(gp._y)}
+    gp.y = y + 1.0
+    g1 = gp._data_gen
+    gp.y = y + 2.0
+    g2 = gp._data_gen
+    assert g0 < g1 < g2
+    gp.x = x + 0.5
+    assert gp._data_gen > g2
+    gen = gp._data_gen
+    gp.s = 0.5                                   # hyperparameters do not touch the observations
+    gp.set_param("w", 0.7)
+    gp.y = gp.y.copy()                           # equal values: the setter is a no-op (gp.py:166-167)
+    assert gp._data_gen == gen
+    # a copy starts its own evaluator and its own generation count
+    for g in (gp.copy(), copy(gp), pickle.loads(pickle.dumps(gp))):
+        assert not hasattr(g, "_batch_ev") and g._data_gen == 0
+
+
+def test_fused_kind_only_for_builtin_formulas():
+    from gaussian_processes_b200.gp import fused_kind
+
+    class Scaled(GaussianKernel):                # overrides the element formula: must not take the CUDA functor
+        def K(self, x1, x2, out=None):
+            return 2.0 * GaussianKernel.K(self, x1, x2, out)
+
+    class Renamed(PeriodicKernel):               # same formulas, extra behaviour elsewhere: fused path is right
+        def describe(self):
+            return "periodic"
+
+    assert fused_kind(GaussianKernel(1, 1)) == 0 and fused_kind(PeriodicKernel(1, 1, 1)) == 1
+    assert fused_kind(Scaled(1, 1)) is None
+    assert fused_kind(Renamed(1, 1, 1)) == 1
+    assert fused_kind(object()) is None
+
+
+def test_fit_mlii_validates_and_reports_nothing_found():
+    import torch
+    from gaussian_processes_b200 import mlii
+    x, y = make_xy()
+    gp = GP(GaussianKernel(1, 1), x, y, s=1)
+    p0 = gp.params.copy()
+
+    def all_bad(th):
+        t = np.full((len(th), 5), np.nan)
+        t[:, 0] = -np.inf
+        t[:, 4] = 1
+        return torch.from_numpy(t)
+    cand = np.array([[1.0, 0.5, 0.1], [2.0, 0.3, 0.2]])
+    res = mlii.fit_MLII(gp, cand, evaluate=all_bad, distributed=False)
+    assert not res.found and res.best_index == -1 and res.best_params is None
+    assert res.best_log_lh == -np.inf and (gp.params == p0).all()          # the GP did not move
+    for bad in ([[0.0, 0.5, 0.1]], [[1.0, -1.0, 0.1]], [[1.0, 0.5, -0.1]], [[1.0, np.nan, 0.1]]):
+        with pytest.raises(ValueError):
+            mlii.fit_MLII(gp, np.array(bad), evaluate=all_bad, distributed=False)
+    with pytest.raises(ValueError):
+        mlii.fit_MLII(gp, np.empty((0, 3)), evaluate=all_bad, distributed=False)
+    with pytest.raises(ValueError):
+        mlii.fit_MLII(gp, np.ones((2, 4)), evaluate=all_bad, distributed=False)

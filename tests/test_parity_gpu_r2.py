@@ -1,0 +1,165 @@
+"""Round-2 parity tests: regressions found by review (stale device copies of x / y in the batched
+evaluator, subclassed built-in kernels), and the BASELINE configs C3 / C4 / C5 at their stated sizes
+against digests produced by the UNMODIFIED reference (tests/golden/make_golden_full.py).
+Tolerance as everywhere: scalars |d|/|ref| <= 1e-9, arrays ||d||_inf <= 1e-9 ||ref||_inf."""
+import numpy as np
+import pytest
+
+import gaussian_processes_b200 as gpb
+from gaussian_processes_b200 import GP, GaussianKernel, PeriodicKernel
+from conftest import golden, assert_parity, synth_xy, RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ review findings
+def test_batch_eval_sees_every_data_update(oracle):
+    """Two assignments of gp.y (or gp.x) between two batch_eval calls: the third array usually takes the
+    id() of the first, so an id-keyed cache would keep evaluating the old observations."""
+    x, y = synth_xy(200, 3)
+    rng = np.random.RandomState(5)
+    cand = np.stack([rng.uniform(0.5, 2, 6), rng.uniform(0.2, 1.2, 6), rng.uniform(0.75, 1.5, 6)], axis=1)
+    gp = GP(GaussianKernel(1.0, 1.0), x, y, s=1.0)
+    l0, g0 = gp.batch_eval(cand)
+    _, o0, og0 = oracle.oracle_fit_mlii(oracle.GAUSSIAN, x, y, cand)
+    assert_parity(l0, o0)
+    for rep in range(3):
+        gp.y = y + 1.0 + rep                      # dropped immediately ...
+        y2 = np.cos(x) * (1.0 + 0.1 * rep) + 0.05 * rng.randn(x.size)
+        gp.y = y2                                 # ... this one may reuse its id
+        l1, g1 = gp.batch_eval(cand)
+        _, o1, og1 = oracle.oracle_fit_mlii(oracle.GAUSSIAN, x, y2, cand)
+        assert_parity(l1, o1, RTOL, "log_lh after y update %d" % rep)
+        assert_parity(g1, og1, RTOL, "grad after y update %d" % rep)
+    x2 = np.sort(rng.uniform(-5, 5, x.size))
+    gp.x = x + 0.25
+    gp.x = x2
+    l2, g2 = gp.batch_eval(cand)
+    _, o2, og2 = oracle.oracle_fit_mlii(oracle.GAUSSIAN, x2, gp.y, cand)
+    assert_parity(l2, o2, RTOL, "log_lh after x update")
+    assert_parity(g2, og2, RTOL, "grad after x update")
+    res = gp.fit_MLII(cand, set_params=False)
+    assert res.best_index == int(np.argmax(o2))
+
+
+def test_subclass_overriding_K_is_not_fused(oracle):
+    """A subclass of a built-in kernel that overrides K / jacobian / hessian must be evaluated through
+    its own methods everywhere (the reference GP only ever calls those methods)."""
+    class Doubled(GaussianKernel):
+        def K(self, x1, x2, out=None):
+            r = GaussianKernel.K(self, x1, x2, out)
+            r *= 2.0
+            return r
+
+        def jacobian(self, x1, x2, out=None):
+            r = GaussianKernel.jacobian(self, x1, x2, out)
+            r *= 2.0
+            return r
+
+        def hessian(self, x1, x2, out=None):
+            r = GaussianKernel.hessian(self, x1, x2, out)
+            r *= 2.0
+            return r
+    x, y = synth_xy(150, 2)
+    h, w, s = 0.9, 0.6, 0.8
+    gp = GP(Doubled(h, w), x, y, s=s)
+    # 2 * h^2 * g(w) == (sqrt(2) h)^2 g(w): the oracle with h' = sqrt(2) h gives the same GP
+    ref = oracle.OracleGP(oracle.GAUSSIAN, (np.sqrt(2.0) * h, w), x, y, s)
+    assert_parity(gp.log_lh, ref.log_lh)
+    assert_parity(gp.Kxx, ref.Kxx, 1e-13)
+    xo = np.linspace(-6, 6, 40)
+    assert_parity(gp.mean(xo), ref.mean(xo))
+    assert_parity(gp.cov(xo), ref.cov(xo))
+    g = gp.dloglh_dtheta
+    r = ref.dloglh_dtheta
+    assert_parity(g[1:], r[1:])                                     # w and s rows are unchanged
+    assert_parity(g[0], r[0] * np.sqrt(2.0))                        # d/dh = sqrt(2) d/dh'
+    llh, _ = gp.batch_eval(np.array([[h, w, s], [1.1, 0.5, 0.9]]))
+    assert_parity(llh[0], ref.log_lh)
+
+
+def test_symbolic_kernel_six_parameters_hessian():
+    """1 + n_p + n_p^2 = 43 slices at n_p = 6: the slice mask no longer fits 32 bits (it used to be
+    truncated silently, leaving most Hessian slices unwritten).  Every slice against sympy/numpy, and
+    the second derivatives of the likelihood through the GP against finite differences of the
+    gradient."""
+    import sympy as sym
+    h1, w1, h2, w2, p, a, d = sym.symbols("h1 w1 h2 w2 p a d")
+    names = ("h1", "w1", "h2", "w2", "p", "a")
+    expr = h1 ** 2 * sym.exp(-d ** 2 / (2 * w1 ** 2)) + h2 ** 2 * sym.exp(-2 * sym.sin(d / (2 * p)) ** 2 / w2 ** 2) \
+        + a ** 2 / (1 + d ** 2)
+    vals = (1.1, 0.6, 0.7, 0.9, 1.3, 0.4)
+    k = gpb.SymbolicKernel(expr, names, vals)
+    rng = np.random.RandomState(9)
+    x1, x2 = rng.uniform(-4, 4, 37), rng.uniform(-4, 4, 29)
+    D_ = x1[:, None] - x2[None, :]
+    syms = (h1, w1, h2, w2, p, a)
+
+    def ev(e):
+        return np.broadcast_to(sym.lambdify((d,) + syms, e, "numpy")(D_, *vals), D_.shape)
+    assert_parity(k(x1, x2), ev(expr), 1e-13, "K")
+    J = k.jacobian(x1, x2)
+    H = k.hessian(x1, x2)
+    assert J.shape == (6, 37, 29) and H.shape == (6, 6, 37, 29)
+    for i, si in enumerate(syms):
+        assert_parity(J[i], ev(sym.diff(expr, si)), 1e-12, "J[%d]" % i)
+        for j, sj in enumerate(syms):
+            assert_parity(H[i, j], ev(sym.diff(expr, si, sj)), 1e-11, "H[%d,%d]" % (i, j))
+    x, y = synth_xy(96, 6)
+    gp = GP(k, x, y, s=0.8)
+    d2 = gp.d2loglh_dtheta2()
+    assert np.isfinite(d2).all() and np.allclose(d2, d2.T, rtol=1e-8, atol=1e-8)
+    th0 = gp.params.copy()
+    for i in (1, 4, 6):                                   # w1, p, s columns by central differences
+        eps = 1e-5
+        tp, tm = th0.copy(), th0.copy()
+        tp[i] += eps
+        tm[i] -= eps
+        gp.params = tp
+        gpl = gp.dloglh_dtheta.copy()
+        gp.params = tm
+        gml = gp.dloglh_dtheta.copy()
+        fd = (gpl - gml) / (2 * eps)
+        assert np.allclose(d2[:, i], fd, rtol=2e-5, atol=1e-6 * np.abs(d2).max()), (i, d2[:, i], fd)
+    gp.params = th0
+    with pytest.raises(ValueError):
+        k.device_slices(None, 0, None, 0, 0, 0, 1 << 43)
+
+
+def test_two_host_threads_share_the_library(oracle):
+    """ctypes releases the GIL inside a call, so two Python threads can be in libgpb200.so at once; the
+    entry points that use process-global staging buffers serialise on an internal lock.  Each thread
+    drives its own GP objects (posterior calls reallocate the shared pinned buffer as sizes grow)."""
+    import threading
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            out = []
+            for rep in range(6):
+                n = 60 + 37 * ((tid + rep) % 4)
+                x, y = synth_xy(n, 10 * tid + rep)
+                kp = (1.0 + 0.1 * tid, 0.4 + 0.05 * rep)
+                gp = GP(GaussianKernel(*kp), x, y, s=0.7)
+                xo = np.linspace(-6, 6, 33 + 300 * (rep % 3))
+                out.append((n, 10 * tid + rep, kp, float(gp.log_lh), gp.dloglh_dtheta.copy(), gp.mean(xo), gp.cov(xo),
+                            gp.batch_eval(np.array([[1.0, 0.5, 0.9], [1.2, 0.4, 1.1]]))[0]))
+            results[tid] = out
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for tid, out in results.items():
+        for n, sd, kp, llh, g, m, c, bl in out:
+            x, y = synth_xy(n, sd)
+            ref = oracle.OracleGP(oracle.GAUSSIAN, kp, x, y, 0.7)
+            xo = np.linspace(-6, 6, m.size)
+            assert_parity(llh, ref.log_lh)
+            assert_parity(g, ref.dloglh_dtheta)
+            assert_parity(m, ref.mean(xo))
+            assert_parity(c, ref.cov(xo))
+            assert_parity(bl[0], oracle.OracleGP(oracle.GAUSSIAN, (1.0, 0.5), x, y, 0.9).log_lh)
