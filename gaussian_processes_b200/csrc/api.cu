@@ -77,7 +77,9 @@ static GpbOption g_options[] = {
     {"potrf_inner", "GPB_POTRF_INNER", 0, false},     // 128-columns per outer Cholesky panel
     {"potrf_lookahead", "GPB_POTRF_LOOKAHEAD", 0, false},   // 0 = panel look-ahead for one matrix of N >= 6144, 1 = always, 2 = off
     {"potrf_panel_rl", "GPB_POTRF_PANEL_RL", 0, false},     // 0 = right-looking panel steps for one matrix, 1 = always, 2 = never
-    {"gemm_impl", "GPB_GEMM_IMPL", 0, false},         // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
+    {"gemm_impl", "GPB_GEMM_IMPL", 0, false},
+    {"potrf_dataflow", "GPB_POTRF_DATAFLOW", 0, false},
+    {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // CTAs sharing the dataflow factorisation's critical path: 8 (default), 4 or 1     // 0 = one matrix of N <= 8192 by the persistent dataflow launch, 1 = whenever batch == 1, 2 = never         // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
 };
 int gpb_get_option(const char* name) {
     for (auto& o : g_options)

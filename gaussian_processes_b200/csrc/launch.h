@@ -65,6 +65,10 @@ int gpb_launch_potrf(double* A, long long n, long long ld, long long sA, int bat
 // n_valid: rows that are not identity pad (0 = n); zero_blocks = false: the caller writes the structural
 // zeros of the inverted diagonal blocks itself (gpb_launch_small_tail does); single_chain: one matrix whose
 // factorisation is not overlapped with others (right-looking panel steps, see potrf.cu)
+// chain.cu: one matrix (2 <= n/128 <= 64) factored by a single persistent dataflow launch
+bool gpb_potrf_dataflow_ok(long long n, int batch);
+int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, long long ldw, double* V,
+                              long long ldv, int* info, cudaStream_t st, long long n_valid);
 int gpb_launch_trtri(const double* L, long long n, long long ld, long long sL, int batch, double* W,
                      long long ldw, long long sW, double* V, long long ldv, long long sV, double* T,
                      long long ldt, long long sT, cudaStream_t st);

@@ -1,0 +1,67 @@
+"""gpb_potrf of one matrix: the persistent dataflow launch (chain.cu) against the launch-sequence
+schedule (potrf.cu) -- same factor, inverted diagonal blocks and info; time of both."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from gaussian_processes_b200 import _lib, engine, device as D
+from conftest import synth_xy
+
+sizes = [int(a) for a in sys.argv[1:]] or [256, 384, 1024, 2048, 4096, 8192]
+for nn in sizes:
+    xx, yy = synth_xy(nn, 0)
+    eng = engine.Engine(engine.GAUSSIAN, (1.0, 0.5), 1.0, xx, yy)
+    res = {}
+    for mode in (2, 0):
+        _lib.set_option("potrf_dataflow", mode)
+        W, V, info = D.zeros(nn, nn), D.zeros(nn, nn), D.izeros(1)
+        best = 1e9
+        for k in range(4):
+            L = eng.build(eng.dx, nn, eng.dx, nn, nn, nn, 1, add_diag=True, pad_identity=True)[0]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            _lib.call("gpb_potrf", D.ptr(L), nn, nn, 0, 1, D.ptr(W), nn, 0, D.ptr(V), nn, 0, D.ptr(info), D.stream_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        res[mode] = (torch.tril(L).clone(), W.clone(), V.clone(), int(info.item()), best)
+        del L, W, V
+    L0, W0, V0, i0, t0 = res[2]
+    L1, W1, V1, i1, t1 = res[0]
+    blk = torch.zeros(nn, nn, dtype=torch.bool, device=L0.device)
+    for b in range(nn // 128):
+        blk[b * 128:(b + 1) * 128, b * 128:(b + 1) * 128] = True
+    out = dict(n=nn, info_old=i0, info_new=i1, ms_old=round(t0, 3), ms_new=round(t1, 3),
+               tflops_old=round(nn ** 3 / 3 / t0 / 1e9, 2), tflops_new=round(nn ** 3 / 3 / t1 / 1e9, 2),
+               dL=float((L0 - L1).abs().max() / L0.abs().max()),
+               dW=float(((W0 - W1) * blk).abs().max() / (W0 * blk).abs().max()),
+               dV=float(((V0 - V1) * blk).abs().max() / (V0 * blk).abs().max()),
+               nan=bool(torch.isnan(L1).any().item()))
+    print(json.dumps(out), flush=True)
+    del eng, res
+_lib.set_option("potrf_dataflow", 0)
+
+# phase clocks of the chain CTA for the last size
+import ctypes
+nn = sizes[-1]
+T = nn // 128
+buf = (ctypes.c_longlong * (T * 8))()
+_lib.lib.gpb_debug_chain_clocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+_lib.lib.gpb_debug_chain_clocks(D.stream_ptr(), buf, T)
+c = np.array(buf[:], dtype=np.int64).reshape(T, 8)
+d = np.diff(c, axis=1)[1:]
+names = ["wait_sub", "trsm", "publish", "wait_diag", "syrk", "diag", "publish2"]
+print("chain phases (cycles, mean over steps 1..):", {n: int(v) for n, v in zip(names, d.mean(axis=0))})
+print("chain phases (cycles, step 1, mid, last):", d[0].tolist(), d[len(d) // 2].tolist(), d[-1].tolist())
+print("step total mean cycles", int((c[1:, 7] - c[1:, 0]).mean()), "whole", int(c[-1, 7] - c[0, 0]))
+nc = 148
+wb = (ctypes.c_longlong * (nc * 4))()
+_lib.lib.gpb_debug_chain_workers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+_lib.lib.gpb_debug_chain_workers(D.stream_ptr(), wb, nc)
+w = np.array(wb[:], dtype=np.int64).reshape(nc, 4)[8:]
+w = w[w[:, 3] > 0]
+print("workers: n=%d tasks/worker mean %.1f max %d | cycles mean: wait %d trsm %d upd %d | per-task busy %d | busiest worker total %d, idlest %d" % (
+    len(w), w[:, 3].mean(), w[:, 3].max(), w[:, 0].mean(), w[:, 1].mean(), w[:, 2].mean(),
+    (w[:, 1] + w[:, 2]).sum() / w[:, 3].sum(), (w[:, 0] + w[:, 1] + w[:, 2]).max(), (w[:, 1] + w[:, 2]).min()))
