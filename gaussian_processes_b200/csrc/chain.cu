@@ -5,53 +5,64 @@
 // diagonal block -> TRSM -> panel update, three dependent kernels of 13-56 us that each use a fraction of
 // the GPU; at N = 4096 that chain is 2.3 of the 3.1 ms while the O(N^3) work needs 0.6 ms at the DMMA peak.
 //
-// Here ONE cooperative launch holds one CTA per SM for the whole factorisation:
-//   CTA 0, the chain:   for k = 0..T-1:  [k > 0: L(k,k-1) = A(k,k-1) W_{k-1}^T ;  A(k,k) -= L(k,k-1) L(k,k-1)^T]
-//                       then L_kk = chol(A_kk), W_kk = L_kk^-1, V_kk = W_kk^T          (diag_block.cuh)
-//                       -- the critical path POTRF(k) -> TRSM(k+1,k) -> SYRK(k+1,k+1) -> POTRF(k+1) never
-//                       leaves the SM and never waits for a kernel boundary;
-//   CTAs 1.., workers:  every other tile task, statically owned (tile (i,j) -> one worker, so the updates of a
-//                       tile are applied in step order without any lock):
-//                         TRSM(i,k)   L(i,k) = A(i,k) W_kk^T                  i >= k+2   needs DIAG[k]
-//                         UPD(i,j,k)  A(i,j) -= L(i,k) L(j,k)^T   i >= j >= k+1, not (k+1,k+1)
-//                                                                             needs LREADY[i][k], LREADY[j][k]
-//   Dependencies travel through release/acquire flags in global memory (DIAG[k], LREADY[i][k], CNT[i][j] =
-//   number of updates tile (i,j) has received).  Every CTA works through its tasks in one global
-//   topological order (by step k, then column), taking a TRSM of its own as soon as it is runnable, so the
-//   earliest unfinished task is always runnable by its owner: no deadlock; all CTAs are co-resident
-//   (cooperative launch), spin loops carry a clock-based time-out that aborts the launch through an error flag.
+// Here ONE cooperative launch holds one CTA (512 threads) per SM for the whole factorisation:
 //
-// Tile product: 128 x 128 x 128 on DMMA.8x8x4, 16 warps of 32 x 32, operands staged by a 4-stage cp.async.cg
-// ring (L2 -> shared memory, never through L1: tiles are produced by other SMs).  The warp -> (row, column)
-// block map is skewed so that every SM sub-partition holds all four column blocks: triangular skipping
-// (TRSM: k <= column) then shortens every sub-partition's DMMA queue alike.
+//   CTAs 0..NG-1, the chain group.  The critical path POTRF(k) -> TRSM(k+1,k) -> SYRK(k+1,k+1) -> POTRF(k+1)
+//       never waits for a kernel boundary.  CTA 0 factors and inverts the diagonal block (diag_block.cuh);
+//       the two tile products between two diagonal blocks -- 21 us on one SM at the DMMA peak, as long as the
+//       diagonal block itself -- are split over the NG CTAs by strips of 128 / NG rows, each CTA holding the
+//       whole second operand in shared memory (one load phase, no ring: K = 128, latency-bound), meeting
+//       through two arrival counters per step.
+//
+//   CTAs NG.., the workers.  Every other tile task, in HALF tiles (64 x 128) so that one SM runs two
+//       independent warp groups of 8 warps: a task's fixed part (C half-tile in, operand prologue, C out,
+//       fence + publish: L2-bandwidth and latency, measured 12.7 k cycles per full tile against 32.8 k of
+//       DMMA work) overlaps the other group's DMMA main loop -- what two co-resident CTAs per SM do for the
+//       GEMM of gemm.cu, inside a kernel whose CTAs must stay one per SM.
+//         TRSM(i,h,k)   L(i,k)[half h] = A(i,k)[half h] W_kk^T              i >= k+2   needs DIAG[k]
+//         UPD(i,h,j,k)  A(i,j)[half h] -= L(i,k)[half h] L(j,k)^T   i >= j >= k+1, not (k+1,k+1)
+//       Half tiles are statically owned (one group applies all updates of a half tile, in step order, without
+//       any lock), dealt out in order of decreasing column so that every step's live set is balanced.
+//
+//   Dependencies travel through release/acquire flags in global memory: DIAG[k], LRH[i][h][k] (half h of
+//   L(i,k) final), CNT[i][h][j] (updates received).  Every group works through its tasks in one global
+//   topological order (step, column, row), taking a TRSM of its own as soon as it is runnable, so the earliest
+//   unfinished task is always runnable by its owner: no deadlock; all CTAs are co-resident (cooperative
+//   launch); spin loops carry a clock-based time-out that aborts the launch through an error flag (info = -999).
+//
+// Tile product: DMMA.8x8x4, warps of 32 x 32, operands staged by a 3-stage cp.async.cg ring (L2 -> shared
+// memory, never through L1: tiles are produced by other SMs).  The warp -> (row, column) block map pairs column
+// blocks (0,3), (1,2) on each SM sub-partition: triangular skipping (TRSM: k <= column) then shortens every
+// sub-partition's DMMA queue alike.
 #include <map>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
 #include "launch.h"
 #include "diag_block.cuh"
+#include "diag_block512.cuh"
 
 namespace {
 
 constexpr int CT = GPB_NB;                  // tile edge
+constexpr int HR = 64;                      // rows of a half tile
 constexpr int CBK = 16;                     // k-chunk of the ring
 constexpr int CLD = CBK + 4;                // padded row stride (doubles): conflict-free 8-byte fragment loads
-constexpr int CSTAGES = 4;
+constexpr int GSTAGES = 3;
 constexpr int CTHREADS = 512;
-constexpr int C_OPER = CT * CLD;            // doubles per operand chunk
-constexpr int C_RING_BYTES = CSTAGES * 2 * C_OPER * 8;          // 163840
-constexpr int C_SMEM_0 = (C_RING_BYTES > DIAG_SMEM) ? C_RING_BYTES : DIAG_SMEM;
-constexpr int C_STRIP_MAX = (GPB_NB + 32) * (GPB_NB + 4) * 8;      // second operand + a 32-row strip
-constexpr int C_SMEM = (C_SMEM_0 > C_STRIP_MAX) ? C_SMEM_0 : C_STRIP_MAX;
-constexpr long long C_TIMEOUT = 4000000000LL;                   // ~2 s of SM clocks
+constexpr int GTHREADS = 256;               // one worker group
+constexpr int G_A = HR * CLD, G_B = CT * CLD, G_STAGE = G_A + G_B;      // doubles
+constexpr int G_RING = GSTAGES * G_STAGE;                               // doubles per group (92160 bytes)
+constexpr int CSLD = CT + 4;                // strip operand row stride (doubles)
+constexpr int C_STRIP_MAX = (CT + 32) * CSLD * 8;                       // second operand + a 32-row strip
+constexpr int C_SMEM_0 = (2 * G_RING * 8 > DIAG_SMEM) ? 2 * G_RING * 8 : DIAG_SMEM;
+constexpr int C_SMEM_1 = (C_SMEM_0 > C_STRIP_MAX) ? C_SMEM_0 : C_STRIP_MAX;
+constexpr int C_SMEM = (C_SMEM_1 > DIAG512_SMEM) ? C_SMEM_1 : DIAG512_SMEM;
+constexpr long long C_TIMEOUT = 4000000000LL;                           // ~2 s of SM clocks
 
 enum { TASK_TRSM = 0, TASK_UPD = 1 };
-struct ChainTask { short type, i, j, k; };
-
-// lower 32x32 blocks of a diagonal tile spread over the sub-partitions (warp w runs on sub-partition w & 3)
-__constant__ signed char c_diag_m[16] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, -1, -1, -1, -1, -1, -1};
-__constant__ signed char c_diag_n[16] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 0, 0, 0, 0, 0};
+constexpr int g_dclk_off = 2 * 160 * 4;       // phase clocks of one diagonal block behind the worker accounting
+struct ChainTask { unsigned char type, h; short i, j, k; };
 
 struct ChainArgs {
     double* A; long long ld;
@@ -60,20 +71,21 @@ struct ChainArgs {
     int* info;
     int T; int n_valid;
     int NG;                     // CTAs of the chain group (CTA 0 = the chain, 1..NG-1 its helpers)
-    int* flags;                 // [0] error | DIAG[T] | LREADY[T*T] | CNT[T*T] | TP[T] | SP[T]
-    const ChainTask* bulk; const int* bulk_off;     // per CTA: UPD tasks in (k, j, i) order
-    const ChainTask* trsm; const int* trsm_off;     // per CTA: TRSM tasks in (k, i) order
+    int diag512;                // 1: full diagonal blocks by the 512-thread body (diag_block512.cuh)
+    int* flags;                 // [0] error | DIAG[T] | TP[T] | SP[T] | LRH[2T*T] | CNT[2T*T]
+    const ChainTask* bulk; const int* bulk_off;     // per worker group: UPD tasks in (k, j, i, h) order
+    const ChainTask* trsm; const int* trsm_off;     // per worker group: TRSM tasks in (k, i, h) order
     long long* clk;             // [T][8] phase clocks of the chain CTA (gpb_debug_chain_clocks)
-    long long* wclk;            // [grid][4] per CTA: cycles waiting | in TRSM tasks | in UPD tasks | tasks
+    long long* wclk;            // [2 * grid][4] per worker group: cycles waiting | in TRSM | in UPD | tasks
 };
 #define CHAIN_STAMP(k, p) do { if (tid == 0) a.clk[(k) * 8 + (p)] = clock64(); } while (0)
 
 __device__ __forceinline__ int* f_diag(const ChainArgs& a, int k) { return a.flags + 1 + k; }
-__device__ __forceinline__ int* f_lready(const ChainArgs& a, int i, int k) { return a.flags + 1 + a.T + i * a.T + k; }
-__device__ __forceinline__ int* f_cnt(const ChainArgs& a, int i, int j) { return a.flags + 1 + a.T + a.T * a.T + i * a.T + j; }
-__device__ __forceinline__ int* f_tp(const ChainArgs& a, int k) { return a.flags + 1 + a.T + 2 * a.T * a.T + k; }
-__device__ __forceinline__ int* f_sp(const ChainArgs& a, int k) { return a.flags + 1 + 2 * a.T + 2 * a.T * a.T + k; }
-__host__ __device__ inline size_t chain_flag_words(int T) { return 1 + 3 * (size_t)T + 2 * (size_t)T * T; }
+__device__ __forceinline__ int* f_tp(const ChainArgs& a, int k) { return a.flags + 1 + a.T + k; }
+__device__ __forceinline__ int* f_sp(const ChainArgs& a, int k) { return a.flags + 1 + 2 * a.T + k; }
+__device__ __forceinline__ int* f_lrh(const ChainArgs& a, int i, int h, int k) { return a.flags + 1 + 3 * a.T + (2 * i + h) * a.T + k; }
+__device__ __forceinline__ int* f_cnt(const ChainArgs& a, int i, int h, int j) { return a.flags + 1 + 3 * a.T + 2 * a.T * a.T + (2 * i + h) * a.T + j; }
+__host__ __device__ inline size_t chain_flag_words(int T) { return 1 + 3 * (size_t)T + 4 * (size_t)T * T; }
 
 // thread 0 only: spin until *flag >= target; false on time-out or when another CTA raised the error flag
 __device__ __forceinline__ bool spin_ge(const int* flag, int target, int* err) {
@@ -89,73 +101,87 @@ __device__ __forceinline__ bool spin_ge(const int* flag, int target, int* err) {
     return true;
 }
 
+// ===========================================================================
+// workers: half-tile tasks by one group of 8 warps (2 x 4 blocks of 32 x 32)
+// ===========================================================================
+__device__ __forceinline__ void group_bar(int grp) {
+    asm volatile("bar.sync %0, 256;\n" ::"r"(2 + grp) : "memory");
+}
+
 template <int ROWS>
-__device__ __forceinline__ void ring_load(double* sdst, const double* g, long long ld, int tid) {
+__device__ __forceinline__ void ring_load(double* sdst, const double* g, long long ld, int ltid) {
 #pragma unroll
-    for (int q = 0; q < ROWS * 8 / CTHREADS; q++) {
-        const int c = tid + q * CTHREADS;
+    for (int q = 0; q < ROWS * 8 / GTHREADS; q++) {
+        const int c = ltid + q * GTHREADS;
         const int row = c >> 3, ch = c & 7;
         cp_async16(sdst + row * CLD + ch * 2, g + (long long)row * ld + ch * 2);
     }
 }
 
-// acc (+)= sum_k Ag[r, k] * Bg[c, k] over K = 128 for this warp's 32 x 32 block (wm, wn); the warp multiplies
-// only k-chunks [0, kt_hi) (triangular B), but every warp walks all chunks (loads and barriers are CTA-wide).
-__device__ __forceinline__ void tile_mm(double (&acc)[4][4][2], const double* Ag, long long lda, const double* Bg,
-                                        long long ldb, int wm, int wn, int kt_hi, double* ring, int tid) {
+// acc += sum_k Ag[r, k] * Bg[c, k], K = 128, for this warp's 32 x 32 block (wm, wn) of a 64 x 128 half tile;
+// the warp multiplies only k-chunks [0, kt_hi), but walks all chunks (loads and barriers are group-wide)
+__device__ __forceinline__ void half_mm(double (&acc)[4][4][2], const double* Ag, long long lda, const double* Bg,
+                                        long long ldb, int wm, int wn, int kt_hi, double* ring, int ltid, int grp) {
     constexpr int NK = CT / CBK;
-    const int lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int lane = ltid & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int s = 0; s < CSTAGES - 1; s++) {
-        ring_load<CT>(ring + s * 2 * C_OPER, Ag + s * CBK, lda, tid);
-        ring_load<CT>(ring + s * 2 * C_OPER + C_OPER, Bg + s * CBK, ldb, tid);
+    for (int s = 0; s < GSTAGES - 1; s++) {
+        ring_load<HR>(ring + s * G_STAGE, Ag + s * CBK, lda, ltid);
+        ring_load<CT>(ring + s * G_STAGE + G_A, Bg + s * CBK, ldb, ltid);
         cp_async_commit();
     }
     for (int kt = 0; kt < NK; kt++) {
-        cp_async_wait<CSTAGES - 2>();
-        __syncthreads();
+        cp_async_wait<GSTAGES - 2>();
+        group_bar(grp);
         {
-            const int nx = kt + CSTAGES - 1;
+            const int nx = kt + GSTAGES - 1;
             if (nx < NK) {
-                const int slot = nx % CSTAGES;
-                ring_load<CT>(ring + slot * 2 * C_OPER, Ag + nx * CBK, lda, tid);
-                ring_load<CT>(ring + slot * 2 * C_OPER + C_OPER, Bg + nx * CBK, ldb, tid);
+                const int slot = nx % GSTAGES;
+                ring_load<HR>(ring + slot * G_STAGE, Ag + nx * CBK, lda, ltid);
+                ring_load<CT>(ring + slot * G_STAGE + G_A, Bg + nx * CBK, ldb, ltid);
             }
             cp_async_commit();
         }
         if (kt >= kt_hi) continue;
-        const double* as = ring + (kt % CSTAGES) * 2 * C_OPER + (wm * 32 + g) * CLD + t;
-        const double* bs = ring + (kt % CSTAGES) * 2 * C_OPER + C_OPER + (wn * 32 + g) * CLD + t;
+        const double* as = ring + (kt % GSTAGES) * G_STAGE + (wm * 32 + g) * CLD + t;
+        const double* bs = ring + (kt % GSTAGES) * G_STAGE + G_A + (wn * 32 + g) * CLD + t;
 #pragma unroll
         for (int kk = 0; kk < CBK / 4; kk++) {
-            double a[4], b[4];
+            double av[4], bv[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * CLD + kk * 4];
+            for (int mi = 0; mi < 4; mi++) av[mi] = as[mi * 8 * CLD + kk * 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = bs[ni * 8 * CLD + kk * 4];
+            for (int ni = 0; ni < 4; ni++) bv[ni] = bs[ni * 8 * CLD + kk * 4];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
         }
     }
     cp_async_wait<0>();
-    __syncthreads();                 // the ring may be reused (next task / the diagonal-block body)
+    group_bar(grp);                  // the ring may be reused by this group's next task
 }
 
-// L(i,k) = A(i,k) W_kk^T, in place.  W_kk is lower triangular: column block wn needs k < 32 (wn + 1).
-__device__ __forceinline__ void task_trsm(const ChainArgs& a, int i, int k, double* ring, int tid) {
-    const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int wm = wid >> 2, wn = (wid + wm) & 3;
-    double* At = a.A + (long long)i * CT * a.ld + (long long)k * CT;
+// warp lw (0..7) of a group -> block (wm, wn); sub-partition lw & 3 holds column blocks {s, 3 - s}
+__device__ __forceinline__ void warp_block(int lw, int& wm, int& wn) {
+    wm = lw >> 2;
+    wn = wm ? 3 - (lw & 3) : (lw & 3);
+}
+
+// L(i,k)[half h] = A(i,k)[half h] W_kk^T, in place.  W_kk lower triangular: column block wn needs k < 32 (wn + 1)
+__device__ __forceinline__ void task_trsm(const ChainArgs& a, int i, int h, int k, double* ring, int ltid, int grp) {
+    const int lw = ltid >> 5, lane = ltid & 31, g = lane >> 2, t = lane & 3;
+    int wm, wn;
+    warp_block(lw, wm, wn);
+    double* At = a.A + ((long long)i * CT + h * HR) * a.ld + (long long)k * CT;
     const double* Wk = a.W + (long long)k * CT * a.ldw + (long long)k * CT;
     double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    tile_mm(acc, At, a.ld, Wk, a.ldw, wm, wn, (wn + 1) * 2, ring, tid);
-    // every thread's loads of the tile are complete (barrier at the end of tile_mm): safe to overwrite
+    half_mm(acc, At, a.ld, Wk, a.ldw, wm, wn, (wn + 1) * 2, ring, ltid, grp);
+    // every thread's loads of the half tile are complete (barrier at the end of half_mm): safe to overwrite
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
@@ -165,20 +191,15 @@ __device__ __forceinline__ void task_trsm(const ChainArgs& a, int i, int k, doub
         }
 }
 
-// A(i,j) -= L(i,k) L(j,k)^T.  Diagonal tiles: only the 32x32 blocks on or below the diagonal.
-__device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int j, int k, double* ring, int tid) {
-    const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+// A(i,j)[half h] -= L(i,k)[half h] L(j,k)^T.  Diagonal tiles: only the 32x32 blocks on or below the diagonal.
+__device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int h, int j, int k, double* ring, int ltid, int grp) {
+    const int lw = ltid >> 5, lane = ltid & 31, g = lane >> 2, t = lane & 3;
     int wm, wn;
-    bool active = true;
-    if (i == j) {
-        wm = c_diag_m[wid]; wn = c_diag_n[wid];
-        if (wm < 0) { active = false; wm = 0; wn = 0; }
-    } else {
-        wm = wid >> 2; wn = (wid + wm) & 3;
-    }
-    const double* Ai = a.A + (long long)i * CT * a.ld + (long long)k * CT;
+    warp_block(lw, wm, wn);
+    const bool active = (i != j) || (wn <= 2 * h + wm);
+    const double* Ai = a.A + ((long long)i * CT + h * HR) * a.ld + (long long)k * CT;
     const double* Aj = a.A + (long long)j * CT * a.ld + (long long)k * CT;
-    double* Ct = a.A + (long long)i * CT * a.ld + (long long)j * CT;
+    double* Ct = a.A + ((long long)i * CT + h * HR) * a.ld + (long long)j * CT;
     // accumulators start at -C: the loads overlap the ring's prologue, the result is -(acc)
     double acc[4][4][2];
 #pragma unroll
@@ -193,7 +214,7 @@ __device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int j, int k
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             }
         }
-    tile_mm(acc, Ai, a.ld, Aj, a.ld, wm, wn, active ? CT / CBK : 0, ring, tid);
+    half_mm(acc, Ai, a.ld, Aj, a.ld, wm, wn, active ? CT / CBK : 0, ring, ltid, grp);
     if (!active) return;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
@@ -204,26 +225,89 @@ __device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int j, int k
         }
 }
 
-// make this CTA's global stores visible, then publish
-// (stores of all threads -> CTA barrier -> one gpu-scope fence + release store: cumulativity carries the
-//  other threads' stores; a fence per thread costs ~1k cycles more)
-__device__ __forceinline__ void publish(int* flag, int value, int tid) {
-    __syncthreads();
-    if (tid == 0) {
+// stores of all threads of the group -> group barrier -> one gpu-scope fence + release store (cumulativity
+// carries the other threads' stores; a fence per thread costs ~1k cycles more)
+__device__ __forceinline__ void publish_group(int* flag, int value, int ltid, int grp) {
+    group_bar(grp);
+    if (ltid == 0) {
         __threadfence();
         st_release(flag, value);
     }
 }
 
-// ===========================================================================
-// The critical path between two diagonal blocks, TRSM(k,k-1) then SYRK(k,k), is 0.625 * 2 * 128^3 * 2 flop:
-// 21 us on ONE SM at the DMMA peak -- as long as the diagonal block itself.  It is therefore split over
-// the NG CTAs of the chain group by rows: each takes a strip of CR = 128 / NG rows of the tile, holds the
-// whole second operand in shared memory (one load phase, no ring: the products are latency-bound, K = 128
-// with two accumulator tiles per warp) and the group meets through two arrival counters per step.
-// ===========================================================================
-constexpr int CSLD = CT + 4;                     // strip operand row stride (doubles)
+__device__ __forceinline__ void worker_group(const ChainArgs& a, double* ring, volatile int* s_act, int ltid, int grp) {
+    int* err = a.flags;
+    const int v = ((int)blockIdx.x - a.NG) * 2 + grp;          // worker group index
+    int bt = a.bulk_off[v];
+    const int bend = a.bulk_off[v + 1];
+    int qt = a.trsm_off[v];
+    const int qend = a.trsm_off[v + 1];
+    long long w_wait = 0, w_trsm = 0, w_upd = 0, w_n = 0;
+    while (bt < bend || qt < qend) {
+        const long long tw0 = clock64();
+        if (ltid < 32) {
+            // The group's first warp picks the next action: an own TRSM as soon as it is runnable (it
+            // unblocks other groups), else the next update in order.  One poll = one parallel round of
+            // acquire loads: lanes 0-1 the TRSM's conditions, lanes 2-4 the update's.
+            const int lane = ltid;
+            ChainTask r = {0, 0, 0, 0, 0}, u = {0, 0, 0, 0, 0};
+            const bool have_r = qt < qend, have_u = bt < bend;
+            if (have_r) r = a.trsm[qt];
+            if (have_u) u = a.bulk[bt];
+            const int* fp = nullptr;
+            int target = 0;
+            if (have_r && lane == 0) { fp = f_cnt(a, r.i, r.h, r.k); target = r.k; }
+            if (have_r && lane == 1) { fp = f_diag(a, r.k); target = 1; }
+            if (have_u && lane == 2) { fp = f_lrh(a, u.i, u.h, u.k); target = 1; }
+            if (have_u && lane == 3) { fp = f_lrh(a, u.j, 0, u.k); target = 1; }
+            // the first half of a diagonal tile only multiplies by rows 0..63 of L(j,k)
+            if (have_u && lane == 4 && !(u.i == u.j && u.h == 0)) { fp = f_lrh(a, u.j, 1, u.k); target = 1; }
+            int act = -1;
+            const long long t0 = clock64();
+            unsigned it = 0;
+            for (;;) {
+                const bool ok = fp ? (ld_acquire(fp) >= target) : true;
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (have_r && (m & 3u) == 3u) { act = 0; break; }
+                if (have_u && (m & 28u) == 28u) { act = 1; break; }
+                if ((++it & 63u) == 0) {
+                    int stop = 0;
+                    if (lane == 0) {
+                        if (ld_acquire(err) != 0) stop = 1;
+                        else if (clock64() - t0 > C_TIMEOUT) { atomicExch(err, 3); stop = 1; }
+                    }
+                    if (__shfl_sync(0xffffffffu, stop, 0)) break;
+                }
+            }
+            if (lane == 0) s_act[grp] = act;
+        }
+        group_bar(grp);
+        const int act = s_act[grp];
+        if (act < 0) return;
+        const long long tw1 = clock64();
+        w_wait += tw1 - tw0;
+        if (act == 0) {
+            const ChainTask r = a.trsm[qt++];
+            task_trsm(a, r.i, r.h, r.k, ring, ltid, grp);
+            publish_group(f_lrh(a, r.i, r.h, r.k), 1, ltid, grp);
+            w_trsm += clock64() - tw1;
+        } else {
+            const ChainTask u = a.bulk[bt++];
+            task_upd(a, u.i, u.h, u.j, u.k, ring, ltid, grp);
+            publish_group(f_cnt(a, u.i, u.h, u.j), u.k + 1, ltid, grp);
+            w_upd += clock64() - tw1;
+        }
+        w_n++;
+    }
+    if (ltid == 0) {
+        a.wclk[v * 4 + 0] = w_wait; a.wclk[v * 4 + 1] = w_trsm;
+        a.wclk[v * 4 + 2] = w_upd; a.wclk[v * 4 + 3] = w_n;
+    }
+}
 
+// ===========================================================================
+// chain group: strips of CR = 128 / NG rows
+// ===========================================================================
 // rows [r0, r0 + CR) of  X = A(k,k-1) W_{k-1}^T  (in place); X strip also left in shared memory (As)
 template <int CR>
 __device__ __forceinline__ void strip_trsm(const ChainArgs& a, int k, int r0, double* Bs, double* As, int tid) {
@@ -304,44 +388,54 @@ __device__ __forceinline__ void strip_syrk(const ChainArgs& a, int k, int r0, do
             make_double2(-acc[mi][0], -acc[mi][1]);
 }
 
-// this CTA's part is stored: count it; the last of `total` arrivals publishes `done_flag` (optional)
-__device__ __forceinline__ void arrive(int* counter, int total, int* done_flag, int tid) {
+__device__ __forceinline__ void publish(int* flag, int value, int tid) {
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        st_release(flag, value);
+    }
+}
+
+// this CTA's part is stored: count it; the last of `total` arrivals publishes the two `done` flags (optional)
+__device__ __forceinline__ void arrive(int* counter, int total, int* done0, int* done1, int tid) {
     __syncthreads();
     if (tid == 0) {
         __threadfence();
         const int old = atomicAdd(counter, 1);
-        if (done_flag && old == total - 1) {
+        if (done0 && old == total - 1) {
             __threadfence();
-            st_release(done_flag, 1);
+            st_release(done0, 1);
+            st_release(done1, 1);
         }
     }
 }
 
 template <int CR>
-__device__ __forceinline__ void chain_group(const ChainArgs& a, double* csm, int* s_act, int tid) {
+__device__ __forceinline__ void chain_group(const ChainArgs& a, double* csm, volatile int* s_act, int tid) {
     int* err = a.flags;
     const int c = blockIdx.x, NG = a.NG, T = a.T;
+    const int r0 = c * CR, h = r0 / HR;
     double* Bs = csm;
     double* As = csm + CT * CSLD;
     for (int k = 0; k < T; k++) {
         if (c == 0) CHAIN_STAMP(k, 0);
         if (k > 0) {
             if (tid == 0)
-                s_act[0] = (spin_ge(f_diag(a, k - 1), 1, err) && spin_ge(f_cnt(a, k, k - 1), k - 1, err)) ? 1 : 0;
+                s_act[0] = (spin_ge(f_diag(a, k - 1), 1, err) && spin_ge(f_cnt(a, k, h, k - 1), k - 1, err)) ? 1 : 0;
             __syncthreads();
             if (!s_act[0]) { if (tid == 0 && c == 0) *a.info = -999; return; }
             if (c == 0) CHAIN_STAMP(k, 1);
-            strip_trsm<CR>(a, k, c * CR, Bs, As, tid);
+            strip_trsm<CR>(a, k, r0, Bs, As, tid);
             if (c == 0) CHAIN_STAMP(k, 2);
-            arrive(f_tp(a, k), NG, f_lready(a, k, k - 1), tid);
+            arrive(f_tp(a, k), NG, f_lrh(a, k, 0, k - 1), f_lrh(a, k, 1, k - 1), tid);
             if (c == 0) CHAIN_STAMP(k, 3);
             if (tid == 0)
-                s_act[1] = (spin_ge(f_tp(a, k), NG, err) && spin_ge(f_cnt(a, k, k), k - 1, err)) ? 1 : 0;
+                s_act[1] = (spin_ge(f_tp(a, k), NG, err) && spin_ge(f_cnt(a, k, h, k), k - 1, err)) ? 1 : 0;
             __syncthreads();
             if (!s_act[1]) { if (tid == 0 && c == 0) *a.info = -999; return; }
             if (c == 0) CHAIN_STAMP(k, 4);
-            strip_syrk<CR>(a, k, c * CR, Bs, As, tid);
-            arrive(f_sp(a, k), NG, nullptr, tid);
+            strip_syrk<CR>(a, k, r0, Bs, As, tid);
+            arrive(f_sp(a, k), NG, nullptr, nullptr, tid);
         }
         if (c != 0) continue;
         if (k > 0) {
@@ -350,12 +444,22 @@ __device__ __forceinline__ void chain_group(const ChainArgs& a, double* csm, int
             if (!s_act[2]) { if (tid == 0) *a.info = -999; return; }
         }
         CHAIN_STAMP(k, 5);
-        if (tid < 256) {
+        {
             const long long o = (long long)k * CT;
             const long long valid = (long long)a.n_valid - o;
             const int nsub = valid >= CT ? 4 : (valid <= 0 ? 0 : (int)((valid + SB - 1) / SB));
-            diag_block_body<true>(a.A + o * a.ld + o, a.ld, a.W + o * a.ldw + o, a.ldw,
-                                  a.V ? a.V + o * a.ldv + o : nullptr, a.ldv, a.info, (int)o, nsub, csm);
+            long long* dclk = (k == 1) ? a.wclk + (size_t)g_dclk_off : nullptr;
+            double* Ak = a.A + o * a.ld + o;
+            double* Wk = a.W + o * a.ldw + o;
+            double* Vk = a.V ? a.V + o * a.ldv + o : nullptr;
+            if (nsub == 4 && a.diag512 == 1)     // full block: the 512-thread body with look-ahead inside the block
+                diag_block_body512<8>(Ak, a.ld, Wk, a.ldw, Vk, a.ldv, a.info, (int)o, csm, dclk);
+            else if (nsub == 4 && a.diag512 == 3) diag_block_body512<1>(Ak, a.ld, Wk, a.ldw, Vk, a.ldv, a.info, (int)o, csm, dclk);
+            else if (nsub == 4 && a.diag512 == 4) diag_block_body512<2>(Ak, a.ld, Wk, a.ldw, Vk, a.ldv, a.info, (int)o, csm, dclk);
+            else if (nsub == 4 && a.diag512 == 5) diag_block_body512<4>(Ak, a.ld, Wk, a.ldw, Vk, a.ldv, a.info, (int)o, csm, dclk);
+            else if (tid < 256)             // identity-padded last block
+                diag_block_body<true>(a.A + o * a.ld + o, a.ld, a.W + o * a.ldw + o, a.ldw,
+                                      a.V ? a.V + o * a.ldv + o : nullptr, a.ldv, a.info, (int)o, nsub, csm);
         }
         CHAIN_STAMP(k, 6);
         publish(f_diag(a, k), 1, tid);
@@ -367,71 +471,16 @@ __global__ void __launch_bounds__(CTHREADS, 1) potrf_dataflow_kernel(const Chain
     extern __shared__ __align__(16) double csm[];
     __shared__ int s_act[4];
     const int tid = threadIdx.x;
-    int* err = a.flags;
-    const int T = a.T;
-
     if ((int)blockIdx.x < a.NG) {
-        // ===================== the chain group =====================
         if (a.NG == 8) chain_group<16>(a, csm, s_act, tid);
         else chain_group<32>(a, csm, s_act, tid);
         return;
     }
-
-    // ===================== workers =====================
-    int bt = a.bulk_off[blockIdx.x];
-    const int bend = a.bulk_off[blockIdx.x + 1];
-    int qt = a.trsm_off[blockIdx.x];
-    const int qend = a.trsm_off[blockIdx.x + 1];
-    long long w_wait = 0, w_trsm = 0, w_upd = 0, w_n = 0;
-    while (bt < bend || qt < qend) {
-        const long long tw0 = clock64();
-        if (tid == 0) {
-            // next action: an own TRSM as soon as it is runnable (it unblocks other CTAs), else the next
-            // update in order; spin on both conditions until one holds
-            int act = -1;
-            const long long t0 = clock64();
-            unsigned it = 0;
-            for (;;) {
-                if (qt < qend) {
-                    const ChainTask r = a.trsm[qt];
-                    if (ld_acquire(f_cnt(a, r.i, r.k)) >= r.k && ld_acquire(f_diag(a, r.k)) != 0) { act = 0; break; }
-                }
-                if (bt < bend) {
-                    const ChainTask u = a.bulk[bt];
-                    if (ld_acquire(f_lready(a, u.i, u.k)) != 0 && ld_acquire(f_lready(a, u.j, u.k)) != 0) { act = 1; break; }
-                }
-                if ((++it & 63u) == 0) {
-                    if (ld_acquire(err) != 0) break;
-                    if (clock64() - t0 > C_TIMEOUT) { atomicExch(err, 3); break; }
-                }
-            }
-            s_act[0] = act;
-        }
-        __syncthreads();
-        const int act = s_act[0];
-        if (act < 0) return;
-        const long long tw1 = clock64();
-        w_wait += tw1 - tw0;
-        if (act == 0) {
-            const ChainTask r = a.trsm[qt++];
-            task_trsm(a, r.i, r.k, csm, tid);
-            publish(f_lready(a, r.i, r.k), 1, tid);
-            w_trsm += clock64() - tw1;
-        } else {
-            const ChainTask u = a.bulk[bt++];
-            task_upd(a, u.i, u.j, u.k, csm, tid);
-            publish(f_cnt(a, u.i, u.j), u.k + 1, tid);
-            w_upd += clock64() - tw1;
-        }
-        w_n++;
-    }
-    if (tid == 0) {
-        a.wclk[blockIdx.x * 4 + 0] = w_wait; a.wclk[blockIdx.x * 4 + 1] = w_trsm;
-        a.wclk[blockIdx.x * 4 + 2] = w_upd; a.wclk[blockIdx.x * 4 + 3] = w_n;
-    }
+    const int grp = tid >> 8;
+    worker_group(a, csm + grp * G_RING, s_act, tid & 255, grp);
 }
 
-// ---- host side: task lists per (T, grid) ------------------------------------------------------------
+// ---- host side: task lists per (T, grid, NG) ------------------------------------------------------------
 struct ChainPlan {
     ChainTask* bulk = nullptr; int* bulk_off = nullptr;
     ChainTask* trsm = nullptr; int* trsm_off = nullptr;
@@ -445,42 +494,46 @@ int build_plan(int T, int G, int NG, ChainPlan* out) {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto it = g_plans.find({{T, G}, NG});
     if (it != g_plans.end()) { *out = it->second; return GPB_OK; }
-    const int nw = G - NG;
-    // Tile (i,j) receives j updates (steps 0..j-1), and at step k exactly the tiles with j > k are live.
-    // Dealing the tiles out in order of decreasing j (boustrophedon over the workers) therefore balances
-    // every live set, i.e. every step of the factorisation, to within one tile per worker.
-    std::vector<int> own((size_t)T * T, NG);
+    const int nv = 2 * (G - NG);            // worker groups
+    // Half tile (i,h,j) receives j updates (steps 0..j-1), and at step k exactly the tiles with j > k are
+    // live.  Dealing the half tiles out in order of decreasing j (boustrophedon over the groups) therefore
+    // balances every live set, i.e. every step of the factorisation, to within one task per group.
+    std::vector<int> own((size_t)2 * T * T, 0);
     {
         long long n = 0;
         for (int j = T - 1; j >= 0; j--)
-            for (int i = j; i < T; i++) {
-                const long long round = n / nw, pos = n % nw;
-                own[(size_t)i * T + j] = NG + (int)((round & 1) ? nw - 1 - pos : pos);
-                n++;
-            }
+            for (int i = j; i < T; i++)
+                for (int h = 0; h < 2; h++) {
+                    const long long round = n / nv, pos = n % nv;
+                    own[((size_t)2 * i + h) * T + j] = (int)((round & 1) ? nv - 1 - pos : pos);
+                    n++;
+                }
     }
-    auto owner = [&](int i, int j) { return own[(size_t)i * T + j]; };
-    std::vector<std::vector<ChainTask>> bulk(G), trsm(G);
+    auto owner = [&](int i, int h, int j) { return own[((size_t)2 * i + h) * T + j]; };
+    std::vector<std::vector<ChainTask>> bulk(nv), trsm(nv);
     for (int k = 0; k + 1 < T; k++) {
-        for (int i = k + 2; i < T; i++) trsm[owner(i, k)].push_back({TASK_TRSM, (short)i, (short)k, (short)k});
+        for (int i = k + 2; i < T; i++)
+            for (int h = 0; h < 2; h++)
+                trsm[owner(i, h, k)].push_back({TASK_TRSM, (unsigned char)h, (short)i, (short)k, (short)k});
         for (int j = k + 1; j < T; j++)
             for (int i = j; i < T; i++) {
-                if (i == k + 1 && j == k + 1) continue;            // the chain's own update
-                bulk[owner(i, j)].push_back({TASK_UPD, (short)i, (short)j, (short)k});
+                if (i == k + 1 && j == k + 1) continue;            // the chain group's own update
+                for (int h = 0; h < 2; h++)
+                    bulk[owner(i, h, j)].push_back({TASK_UPD, (unsigned char)h, (short)i, (short)j, (short)k});
             }
     }
     auto upload = [&](std::vector<std::vector<ChainTask>>& lists, ChainTask** dt, int** doff) -> int {
         std::vector<ChainTask> flat;
-        std::vector<int> off(G + 1, 0);
-        for (int g = 0; g < G; g++) {
+        std::vector<int> off(nv + 1, 0);
+        for (int g = 0; g < nv; g++) {
             off[g] = (int)flat.size();
             flat.insert(flat.end(), lists[g].begin(), lists[g].end());
         }
-        off[G] = (int)flat.size();
+        off[nv] = (int)flat.size();
         GPB_CUDA(cudaMalloc(dt, (flat.size() + 1) * sizeof(ChainTask)));
-        GPB_CUDA(cudaMalloc(doff, (G + 1) * sizeof(int)));
+        GPB_CUDA(cudaMalloc(doff, (nv + 1) * sizeof(int)));
         if (!flat.empty()) GPB_CUDA(cudaMemcpy(*dt, flat.data(), flat.size() * sizeof(ChainTask), cudaMemcpyHostToDevice));
-        GPB_CUDA(cudaMemcpy(*doff, off.data(), (G + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        GPB_CUDA(cudaMemcpy(*doff, off.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice));
         return GPB_OK;
     };
     ChainPlan p;
@@ -492,6 +545,22 @@ int build_plan(int T, int G, int NG, ChainPlan* out) {
     *out = p;
     return GPB_OK;
 }
+
+int g_num_sms = 0;
+int chain_init() {
+    static bool done = false;
+    if (done) return GPB_OK;
+    int dev = 0, coop = 0;
+    GPB_CUDA(cudaGetDevice(&dev));
+    GPB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    GPB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GPB_REQUIRE(coop != 0, "device does not support cooperative launches");
+    GPB_CUDA(cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
+    done = true;
+    return GPB_OK;
+}
+
+size_t chain_pool_words(int T) { return (chain_flag_words(T) + 1) / 2 * 2 + (size_t)T * 16 + (size_t)(g_dclk_off + 200) * 2; }
 
 }  // namespace
 
@@ -506,29 +575,22 @@ bool gpb_potrf_dataflow_ok(long long n, int batch) {
 int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, long long ldw, double* V,
                               long long ldv, int* info, cudaStream_t st, long long n_valid) {
     const int T = (int)(n / GPB_NB);
-    static int num_sms = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        int dev = 0, coop = 0;
-        GPB_CUDA(cudaGetDevice(&dev));
-        GPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        GPB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        GPB_REQUIRE(coop != 0, "device does not support cooperative launches");
-        GPB_CUDA(cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
-        attr_set = true;
-    }
-    const long long ntiles = (long long)T * (T + 1) / 2;
+    GPB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && ld % 2 == 0, "A must be 16-byte aligned with an even leading dimension");
+    int stt = chain_init();
+    if (stt) return stt;
+    const int num_sms = g_num_sms;
+    const long long nhalf = (long long)T * (T + 1);                // half tiles
     int NG = gpb_get_option("chain_group");          // CTAs sharing the critical path (4 or 8)
     if (NG != 4 && NG != 8) NG = 8;
     GPB_REQUIRE(num_sms >= 2 * NG, "device too small for the dataflow factorisation");
-    int G = (int)((ntiles + NG < (long long)num_sms) ? ntiles + NG : num_sms);
+    int G = (int)(((nhalf + 1) / 2 + NG < (long long)num_sms) ? (nhalf + 1) / 2 + NG : num_sms);
     if (G < NG + 1) G = NG + 1;
     ChainPlan plan;
-    int stt = build_plan(T, G, NG, &plan);
+    stt = build_plan(T, G, NG, &plan);
     if (stt) return stt;
     // flag words: one grow-only set per stream (two factorisations on one stream are serialised anyway)
-    // (+ the chain's phase clocks, 8 per step, behind the flags)
-    const size_t nfl = (chain_flag_words(T) + 1) / 2 * 2 + (size_t)T * 16 + (size_t)num_sms * 8;
+    // (+ the chain's phase clocks, 8 per step, and the workers' accounting behind the flags)
+    const size_t nfl = chain_pool_words(T);
     int* flags = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_plan_mu);
@@ -550,6 +612,8 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     a.clk = reinterpret_cast<long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2);
     a.wclk = a.clk + (size_t)T * 8;
     a.NG = NG;
+    a.diag512 = gpb_get_option("chain_diag");           // 0/1 default body, 2 the 256-thread body, 3.. experiments
+    if (a.diag512 == 0) a.diag512 = 1;
     void* args[] = {(void*)&a};
     GpbProfScope prof(GPB_KC_GEMM, st);
     GPB_CUDA(cudaLaunchCooperativeKernel((const void*)potrf_dataflow_kernel, dim3((unsigned)G), dim3(CTHREADS), args,
@@ -558,41 +622,80 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     return GPB_OK;
 }
 
-// phase clocks (SM cycles) of the chain CTA in the last dataflow factorisation on `stream`:
-// out[k*8 + p], p = 0 step start | 1 sub-diagonal tile ready | 2 TRSM done | 3 published | 4 diagonal tile
-// ready | 5 SYRK done | 6 diagonal block done | 7 published.  Returns T (steps) or < 0.
-extern "C" int gpb_debug_chain_clocks(void* stream, long long* out, int max_steps) {
+static int chain_debug_pool(void* stream, int** flags, int* T) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int* flags = nullptr;
-    int T = 0;
     {
         std::lock_guard<std::mutex> lk(g_plan_mu);
         auto it = g_flag_pool.find(st);
         if (it == g_flag_pool.end() || !g_last_T.count(st)) { gpb_set_error("no dataflow factorisation ran on this stream"); return GPB_ERR_ARG; }
-        flags = it->second.first;
-        T = g_last_T[st];
+        *flags = it->second.first;
+        *T = g_last_T[st];
     }
     GPB_CUDA(cudaStreamSynchronize(st));
+    return GPB_OK;
+}
+
+// phase clocks (SM cycles) of the chain CTA in the last dataflow factorisation on `stream`:
+// out[k*8 + p], p = 0 step start | 1 sub-diagonal tile ready | 2 TRSM done | 3 published | 4 diagonal tile
+// ready | 5 SYRK done | 6 diagonal block done | 7 published.  Returns T (steps) or < 0.
+extern "C" int gpb_debug_chain_clocks(void* stream, long long* out, int max_steps) {
+    int* flags = nullptr;
+    int T = 0;
+    int stt = chain_debug_pool(stream, &flags, &T);
+    if (stt) return stt;
     const int n = T < max_steps ? T : max_steps;
     const long long* clk = reinterpret_cast<const long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2);
     GPB_CUDA(cudaMemcpy(out, clk, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return T;
 }
 
-// per-CTA accounting of the same launch: out[cta*4 + {0 cycles waiting, 1 in TRSM tasks, 2 in UPD tasks, 3 tasks}]
-extern "C" int gpb_debug_chain_workers(void* stream, long long* out, int max_ctas) {
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// per-worker-group accounting of the same launch: out[v*4 + {0 cycles waiting, 1 in TRSM, 2 in UPD, 3 tasks}]
+extern "C" int gpb_debug_chain_workers(void* stream, long long* out, int max_groups) {
     int* flags = nullptr;
     int T = 0;
-    {
-        std::lock_guard<std::mutex> lk(g_plan_mu);
-        auto it = g_flag_pool.find(st);
-        if (it == g_flag_pool.end() || !g_last_T.count(st)) { gpb_set_error("no dataflow factorisation ran on this stream"); return GPB_ERR_ARG; }
-        flags = it->second.first;
-        T = g_last_T[st];
-    }
-    GPB_CUDA(cudaStreamSynchronize(st));
+    int stt = chain_debug_pool(stream, &flags, &T);
+    if (stt) return stt;
+    if (max_groups > (g_dclk_off + 200) / 4) max_groups = (g_dclk_off + 200) / 4;
     const long long* clk = reinterpret_cast<const long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2) + (size_t)T * 8;
-    GPB_CUDA(cudaMemcpy(out, clk, (size_t)max_ctas * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    GPB_CUDA(cudaMemcpy(out, clk, (size_t)max_groups * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
     return T;
+}
+
+// ---- micro-benchmark of the half-tile task (no flags): both groups of every CTA repeat UPD / TRSM ----------
+namespace {
+__global__ void __launch_bounds__(CTHREADS, 1) chain_tile_bench_kernel(const ChainArgs a, int reps, int mode, long long* out) {
+    extern __shared__ __align__(16) double csm[];
+    const int tid = threadIdx.x, grp = tid >> 8, ltid = tid & 255;
+    // tiles of CTA c: rows 3c + {0, 1, 2}; L_i = (2,0), L_j = (1,0), C = (2,1) of a [3 * grid * 128, 384] matrix
+    ChainArgs b = a;
+    b.A = a.A + (long long)blockIdx.x * 3 * CT * a.ld;
+    if (grp == 1 && (mode & 2)) {           // stagger the groups by half a task
+        const long long ts = clock64();
+        while (clock64() - ts < 20000) {}
+    }
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r++) {
+        if ((mode & 1) == 0) task_upd(b, 2, grp, 1, 0, csm + grp * G_RING, ltid, grp);
+        else task_trsm(b, 2, grp, 0, csm + grp * G_RING, ltid, grp);
+        publish_group(a.flags + 1 + blockIdx.x * 2 + grp, r, ltid, grp);
+    }
+    if (ltid == 0) out[blockIdx.x * 2 + grp] = clock64() - t0;
+}
+}  // namespace
+
+// cycles for `reps` half-tile tasks per worker group.  A: device [3 * grid * 128, 384] (ld >= 384), W: [128, >= 128]
+extern "C" int gpb_debug_tile_bench(double* A, long long ld, double* W, long long ldw, int grid, int reps, int mode,
+                                    int* flags, long long* out_dev, void* stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CUDA(cudaFuncSetAttribute(chain_tile_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
+        attr_set = true;
+    }
+    ChainArgs a;
+    a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = nullptr; a.ldv = 0; a.info = nullptr; a.T = 3; a.n_valid = 0;
+    a.NG = 8; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
+    a.clk = nullptr; a.wclk = nullptr;
+    chain_tile_bench_kernel<<<grid, CTHREADS, C_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(a, reps, mode, out_dev);
+    GPB_LAUNCH_CHECK("chain_tile_bench_kernel");
+    return GPB_OK;
 }

@@ -8,7 +8,10 @@ import torch
 from gaussian_processes_b200 import _lib, engine, device as D
 from conftest import synth_xy
 
-sizes = [int(a) for a in sys.argv[1:]] or [256, 384, 1024, 2048, 4096, 8192]
+sizes = [int(a) for a in sys.argv[1:] if not a.startswith("d")] or [256, 384, 1024, 2048, 4096, 8192]
+for a in sys.argv[1:]:
+    if a.startswith("d"):
+        _lib.set_option("chain_diag", int(a[1:]))
 for nn in sizes:
     xx, yy = synth_xy(nn, 0)
     eng = engine.Engine(engine.GAUSSIAN, (1.0, 0.5), 1.0, xx, yy)
@@ -56,12 +59,18 @@ names = ["wait_sub", "trsm", "publish", "wait_diag", "syrk", "diag", "publish2"]
 print("chain phases (cycles, mean over steps 1..):", {n: int(v) for n, v in zip(names, d.mean(axis=0))})
 print("chain phases (cycles, step 1, mid, last):", d[0].tolist(), d[len(d) // 2].tolist(), d[-1].tolist())
 print("step total mean cycles", int((c[1:, 7] - c[1:, 0]).mean()), "whole", int(c[-1, 7] - c[0, 0]))
-nc = 148
+nc = 296 + 24 + 50        # 2 * 148 worker-group rows + the diagonal block's phase clocks at [320, 324)
 wb = (ctypes.c_longlong * (nc * 4))()
 _lib.lib.gpb_debug_chain_workers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 _lib.lib.gpb_debug_chain_workers(D.stream_ptr(), wb, nc)
-w = np.array(wb[:], dtype=np.int64).reshape(nc, 4)[8:]
+w = np.array(wb[:], dtype=np.int64).reshape(nc, 4)
+dc = w[320:323].reshape(-1)
+arr = w[328:368].reshape(-1)[:160].reshape(10, 16) - dc[0]
+names = ["S0", "C0", "S1", "C1", "S2", "C2", "S3", "T1", "T2", "T3"]
+for ph in range(10):
+    print("  %s warp arrivals (cycles since block start):" % names[ph], arr[ph].tolist())
+w = w[:296]
 w = w[w[:, 3] > 0]
-print("workers: n=%d tasks/worker mean %.1f max %d | cycles mean: wait %d trsm %d upd %d | per-task busy %d | busiest worker total %d, idlest %d" % (
+print("worker groups: n=%d tasks/group mean %.1f max %d | cycles mean: wait %d trsm %d upd %d | per half-tile task busy %d | busiest group total %d, least busy %d" % (
     len(w), w[:, 3].mean(), w[:, 3].max(), w[:, 0].mean(), w[:, 1].mean(), w[:, 2].mean(),
     (w[:, 1] + w[:, 2]).sum() / w[:, 3].sum(), (w[:, 0] + w[:, 1] + w[:, 2]).max(), (w[:, 1] + w[:, 2]).min()))
