@@ -564,11 +564,12 @@ size_t chain_pool_words(int T) { return (chain_flag_words(T) + 1) / 2 * 2 + (siz
 
 }  // namespace
 
-// The largest T the dataflow factorisation takes (N = 8192): beyond it the trailing matrix no longer
+// The largest T the dataflow factorisation takes (N = 6144; measured 4.80 vs 5.72 ms there, 9.9 vs 9.3 ms at
+// N = 8192): beyond it the trailing matrix no longer
 // lives in L2 and the K = 128 updates re-stream it from HBM every step; potrf.cu's look-ahead panels win.
 bool gpb_potrf_dataflow_ok(long long n, int batch) {
     const long long T = n / GPB_NB;
-    return batch == 1 && T >= 2 && T <= 64;
+    return batch == 1 && T >= 2 && T <= 48;
 }
 
 // zero_blocks and info initialisation are the caller's (gpb_launch_potrf) business
