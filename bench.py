@@ -358,6 +358,11 @@ def run_ours(args):
                      "note": "public API on a fitted GP (factor + L^-1 cached), host xo in, numpy out "
                              "(cov includes the D2H of the M x M result)"}
 
+    # ---- BASELINE config C3 on N GPUs: test points sharded over the ranks (strong scaling: M fixed) ----
+    sharded = None
+    if not args.no_sharded:
+        sharded = posterior_sharded(world, rank, sync)
+
     # ---- BASELINE configs[0], the reference's own CPU-runnable case: N=50, one GP object -------
     # cold log_lh + dloglh_dtheta + mean + cov at 100 test points through the public API; the
     # reference's path (oracle/_ref + scipy/numpy) timed beside it on the host cores
@@ -412,12 +417,87 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if posterior is not None:
             line["posterior"] = posterior
+        if sharded is not None:
+            line["posterior_sharded"] = sharded
         if small is not None:
             line["small_gp"] = small
         emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def posterior_sharded(world, rank, sync):
+    """BASELINE config C3: PeriodicKernel(1,1,1), s=1, N=8192, posterior at M=16384 test points partitioned
+    over the ranks (gaussian_processes_b200.sharded_posterior, cov_layout="lower"): each rank computes its
+    rows of Z = K(xo,x) L^-T, ONE all-gather of Z over NVLink, then its block rows of the lower triangle of
+    cov.  M is fixed: strong scaling.  Every rank holds a fitted GP (factor + L^-1: `fit_ms`, each rank
+    redundantly -- fit once, predict many)."""
+    import torch
+    import torch.distributed as dist
+    import gaussian_processes_b200 as gpb
+    n, m = 8192, 16384
+    x, y = synth_xy(n, 0)
+    xo = np.linspace(-2 * np.pi, 2 * np.pi, m)
+
+    def maxtime(t):
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+    gp = gpb.GP(gpb.PeriodicKernel(1.0, 1.0, 1.0), x, y, s=1.0)
+    sync()
+    t0 = time.perf_counter()
+    llh = gp.log_lh
+    gp._engine().inv_factor()
+    torch.cuda.synchronize()
+    fit_ms = maxtime(time.perf_counter() - t0) * 1e3
+    kw = dict(cov_layout="lower")
+    gpb.sharded_posterior(gp, xo, **kw)                              # warm: allocator, page-locked pool, NCCL
+    t_mean, t_dev, t_e2e = [], [], []
+    for rep in range(3):
+        xr = xo + 1e-9 * rep
+        sync()
+        t0 = time.perf_counter()
+        mean, _, plan = gpb.sharded_posterior(gp, xr, want_cov=False, **kw)
+        torch.cuda.synchronize()
+        t_mean.append(maxtime(time.perf_counter() - t0))
+        sync()
+        t0 = time.perf_counter()
+        _, pd, _ = gpb.sharded_posterior(gp, xr, host=False, **kw)
+        torch.cuda.synchronize()
+        t_dev.append(maxtime(time.perf_counter() - t0))
+        del pd
+        sync()
+        t0 = time.perf_counter()
+        _, ph, _ = gpb.sharded_posterior(gp, xr, **kw)
+        torch.cuda.synchronize()
+        t_e2e.append(maxtime(time.perf_counter() - t0))
+        d2h = sum(p[2].nbytes for p in ph)
+        del ph
+    tm = {}
+    sync()
+    gpb.sharded_posterior(gp, xo, host=False, timings=tm, **kw)
+    parts = {k: maxtime(v) * 1e3 for k, v in tm.items() if k != "allgather_bytes"}
+    npad = 8192
+    flops = (float(n) ** 2 * m + float(n) * m * m / 2.0 * (1.0 + 1.0 / plan.nb)) * 2.0 / 2.0 * 2.0 / 2.0
+    # N^2 M (Z = K W^T, W triangular: N^2 M multiply-adds = 2 * N^2 M / 2 flop) + N M^2 (1 + 1/nb) / 2 * 2 flop
+    flops = float(n) ** 2 * m + float(n) * m * m * (1.0 + 1.0 / plan.nb)
+    return {"workload": "C3: PeriodicKernel(1,1,1), s=1, N=%d; posterior at M=%d test points sharded over %d GPU(s)" % (n, m, world),
+            "scaling": "strong", "n": n, "m": m, "n_gpus": world, "blocks": plan.nb, "block_points": plan.bs,
+            "fit_ms_each_rank": fit_ms, "log_lh": float(llh),
+            "mean_test_pts_per_s_e2e": m / min(t_mean), "mean_ms_e2e": min(t_mean) * 1e3,
+            "cov_test_pts_per_s_device": m / min(t_dev), "cov_ms_device": min(t_dev) * 1e3,
+            "cov_test_pts_per_s_e2e": m / min(t_e2e), "cov_ms_e2e": min(t_e2e) * 1e3,
+            "cov_d2h_bytes_per_rank": int(d2h),
+            "cov_e2e_note": "e2e = device time + the D2H of this rank's lower panels into page-locked numpy arrays "
+                            "(PCIe-bound: %.2f GB per rank)" % (d2h / 1e9),
+            "cov_tflops_device": flops / min(t_dev) / 1e12,
+            "collective": {"op": "all_gather_into_tensor of Z (NCCL over NVLink)" if world > 1 else "none (one rank)",
+                           "bytes_total": int(tm.get("allgather_bytes", 0)), "ms": parts.get("allgather")},
+            "phase_ms": parts,
+            "note": "times are max over ranks; mean/cov e2e take host xo in and return host arrays; the result "
+                    "of cov stays sharded (block rows of the lower triangle, (1 + 1/%d)/2 of M^2 doubles in total)" % plan.nb}
 
 
 _REAL_STDOUT = None
@@ -454,6 +534,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-posterior", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the C3 posterior with test points sharded over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -484,6 +484,33 @@ class Engine(object):
                 yield r0, r1
         return self._rows_out(C, mb, m, blocks(), host)
 
+    # ------------------------------------------------------------------ test points sharded over GPUs
+    def z_block(self, dxo_block, mb, bs):
+        """Z_b = K(xo_b, x) L^-T for one block of test points, zero rows beyond ``mb``: [bs, npad] on the
+        device -- N^2 bs flop (W lower triangular).  The unit a rank contributes to the all-gather."""
+        W, _ = self.inv_factor()
+        K = self.build(dxo_block, mb, self.dx, self.n, bs, self.npad, 1)[0]
+        Z = D.empty(bs, self.npad)
+        self.gemm(K, W, Z, bs, self.npad, self.npad, b_tri=1)
+        return Z
+
+    def cov_panel(self, dxo, m, b, bs, zget):
+        """Block row b of the LOWER triangle of cov(xo): C[lo:hi, 0:hi] = K(xo_b, xo[:hi]) - Z_b Z[:hi]^T with
+        lo = b bs (``zget(c)`` -> Z_c on this device).  Blocks left of the diagonal are dense products, the
+        diagonal block computes its lower tiles and mirrors them, nothing right of it is touched: summed over
+        all block rows that is N M^2 / 2 flop + the diagonal blocks -- half the row-shard form.
+        Returns the device tensor [bs, (b + 1) bs] (valid part [:hi - lo, :hi])."""
+        lo = b * bs
+        hi = min(m, lo + bs)
+        width = (b + 1) * bs
+        C = self.build(dxo[lo:hi], hi - lo, dxo[:hi], hi, bs, width, 1)[0]
+        Zb = zget(b)
+        for c in range(b):
+            self.gemm(Zb, zget(c), C[:, c * bs:(c + 1) * bs], bs, bs, self.npad, alpha=-1.0, beta=1.0)
+        Cd = C[:, b * bs:(b + 1) * bs]
+        self.gemm(Zb, Zb, Cd, bs, bs, self.npad, alpha=-1.0, beta=1.0, lower_only=1, Ct=Cd)
+        return C
+
     def solve_residual(self):
         """max |Kxx alpha - y| / max |y| computed on the device with regenerated kernel tiles
         (size-independent check of the factorisation + solves)."""

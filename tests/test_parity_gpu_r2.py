@@ -295,3 +295,32 @@ def test_c5_n32768_full_size_residuals():
         colj = k(xo, xo[j:j + 1])[:, 0] - D.to_host(out)
         assert np.max(np.abs(c[:, j] - colj)) <= RTOL * scale, j
     assert np.max(np.abs(c[17] - c[:, 17])) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("n,m,kparams", [(300, 700, (1.0, 0.5)), (257, 2500, (1.0, 1.0, 1.3)), (64, 5, (0.8, 0.3))])
+def test_sharded_posterior_lower_panels_vs_oracle(oracle, n, m, kparams):
+    """cov_layout="lower" on one GPU: the panels tile the lower triangle of cov(xo) and agree with the
+    oracle's explicit-inverse covariance (normwise) and with GP.cov; gather_cov assembles the full matrix."""
+    x, y = synth_xy(n, 3)
+    xo = np.linspace(-6, 6, m)
+    gp = GP(make_k(kparams), x, y, s=0.9)
+    ref = oracle.OracleGP(oracle.GAUSSIAN if len(kparams) == 2 else oracle.PERIODIC, kparams, x, y, 0.9)
+    rc, rm = ref.cov(xo), ref.mean(xo)
+    scale = np.max(np.abs(rc))
+    mean, panels, plan = gpb.sharded_posterior(gp, xo, cov_layout="lower", distributed=False)
+    assert_parity(mean, rm)
+    covered = np.zeros((m, m), dtype=bool)
+    for lo, hi, P in panels:
+        assert P.shape == (hi - lo, hi)
+        assert np.max(np.abs(P - rc[lo:hi, :hi])) <= RTOL * scale
+        covered[lo:hi, :hi] = True
+    assert covered[np.tril_indices(m)].all()
+    _, full, _ = gpb.sharded_posterior(gp, xo, cov_layout="lower", gather_cov=True, distributed=False)
+    assert np.max(np.abs(full - rc)) <= RTOL * scale
+    assert np.max(np.abs(full - gp.cov(xo))) <= 1e-12 * scale
+    _, dev_panels, _ = gpb.sharded_posterior(gp, xo, cov_layout="lower", host=False, distributed=False)
+    assert all(p[2].is_cuda for p in dev_panels)
+
+
+def make_k(kparams):
+    return GaussianKernel(*kparams) if len(kparams) == 2 else PeriodicKernel(*kparams)
