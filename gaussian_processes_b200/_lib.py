@@ -70,6 +70,11 @@ _PROTOS = {
     "gpb_post_cov_scratch_doubles": (c_size_t, [_i64, _i64]),
     "gpb_post_cov_host": (c_int, [c_int, dp, vp, _i64, vp, _i64, vp, _i64, vp, vp, _i64, vp]),
     "gpb_kernel_slices_host": (c_int, [c_int, c_uint, vp, vp, _i64, vp, _i64, dp]),
+    "gpb_gp_c_log_lh": (c_int, [vp, vp, vp, _i64, dp]),
+    "gpb_gp_c_dloglh_dtheta": (c_int, [vp, vp, vp, vp, c_double, _i64, _i64, vp]),
+    "gpb_gp_c_dlh_dtheta": (c_int, [vp, vp, vp, vp, c_double, c_double, _i64, _i64, vp]),
+    "gpb_gp_c_d2lh_dtheta2": (c_int, [vp, vp, vp, vp, vp, c_double, c_double, vp, _i64, _i64, vp]),
+    "gpb_gp_c_dm_dtheta": (c_int, [vp, vp, vp, vp, vp, c_double, _i64, _i64, _i64, vp]),
     "gpb_microbench_fp64": (c_int, [c_int, c_int, dp, dp]),
     "gpb_microbench_latency": (c_int, [dp]),
     "gpb_set_option": (c_int, [c_char_p, c_int]),

@@ -19,6 +19,7 @@ static thread_local char g_err[512] = "";
 // that only enqueue kernels on the caller's stream do not take it.
 static std::recursive_mutex g_api_mu;
 #define GPB_API_LOCK std::lock_guard<std::recursive_mutex> gpb_api_guard(g_api_mu)
+std::recursive_mutex& gpb_api_mutex() { return g_api_mu; }     // for the other translation units' host entry points
 
 void gpb_set_error(const char* fmt, ...) {
     va_list ap;

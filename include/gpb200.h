@@ -228,6 +228,28 @@ int gpb_periodic_d2K_dpdh(double* out, const double* x1, int64_t n1, const doubl
 int gpb_periodic_d2K_dpdw(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
 int gpb_periodic_d2K_dpdp(double* out, const double* x1, int64_t n1, const double* x2, int64_t n2, double h, double w, double p);
 
+/* ---- gp/ext/gp_c.pyx as host-pointer entry points --------------------------------------
+ * Exactly the reference's argument lists (C-contiguous float64 host arrays; the shapes the
+ * Cython signatures imply are passed as n_p = kernel parameters, n = observations, m = test
+ * points), outputs written in place, no Python / torch on the path:
+ *   gp_c.log_lh(y, K, Kiy) -> float                                  gp_c.pyx:17-31
+ *   gp_c.dloglh_dtheta(y, Ki, Kj, Kiy, s, dloglh)                    gp_c.pyx:34-49
+ *   gp_c.dlh_dtheta(y, Ki, Kj, Kiy, s, lh, dlh)                      gp_c.pyx:52-67
+ *   gp_c.d2lh_dtheta2(y, Ki, Kj, Kh, Kiy, s, lh, dlh, d2lh)          gp_c.pyx:70-111
+ *   gp_c.dm_dtheta(y, Ki, Kj, Kjxo, Kxox, s, dm)                     gp_c.pyx:114-131
+ * Kj: [n_p, n, n]; Kh: [n_p, n_p, n, n]; Kjxo: [n_p, m, n]; Kxox: [m, n]; dloglh, dlh: [n_p + 1];
+ * d2lh: [n_p + 1, n_p + 1]; dm: [n_p + 1, m].  log|K| comes from a Cholesky of K (the reference
+ * takes an LU slogdet, gp_c.pyx:21): a K that is not positive definite gives -inf.            */
+int gpb_gp_c_log_lh(const double* y, const double* K, const double* Kiy, int64_t n, double* llh);
+int gpb_gp_c_dloglh_dtheta(const double* y, const double* Ki, const double* Kj, const double* Kiy, double s,
+                           int64_t n_p, int64_t n, double* dloglh);
+int gpb_gp_c_dlh_dtheta(const double* y, const double* Ki, const double* Kj, const double* Kiy, double s, double lh,
+                        int64_t n_p, int64_t n, double* dlh);
+int gpb_gp_c_d2lh_dtheta2(const double* y, const double* Ki, const double* Kj, const double* Kh, const double* Kiy,
+                          double s, double lh, const double* dlh, int64_t n_p, int64_t n, double* d2lh);
+int gpb_gp_c_dm_dtheta(const double* y, const double* Ki, const double* Kj, const double* Kjxo, const double* Kxox,
+                       double s, int64_t n_p, int64_t n, int64_t m, double* dm);
+
 /* ---- measurement helpers ----------------------------------------------------------
  * FP64 tensor (DMMA.8x8x4) and FP64 FMA issue-rate microbenchmarks: the roofline
  * denominator for the factorisation (MEASURED_PEAKS.json has no fp64 figure).          */
@@ -244,7 +266,10 @@ int64_t gpb_launch_count(void);
  *   "gemm_bm"      (GPB_GEMM_BM)      64 (two CTAs per SM) or 128 row tiles in the DMMA GEMM
  *   "potrf_inner"  (GPB_POTRF_INNER)  128-columns per outer Cholesky panel
  *   "potrf_lookahead" (GPB_POTRF_LOOKAHEAD) panel look-ahead of a single factorisation: 0 auto (N >= 6144), 1 on, 2 off
- *   "gemm_impl"    (GPB_GEMM_IMPL)    0 TMA + mbarrier operand pipeline, 1 cp.async pipeline                */
+ *   "gemm_impl"    (GPB_GEMM_IMPL)    0 TMA + mbarrier operand pipeline, 1 cp.async pipeline
+ *   "potrf_dataflow" (GPB_POTRF_DATAFLOW) one matrix by the persistent dataflow launch: 0 auto (256 <= N <= 6144), 1 whenever batch == 1, 2 never
+ *   "chain_group"  (GPB_CHAIN_GROUP)  CTAs sharing the dataflow factorisation's critical path: 8 (default) or 4
+ *   "chain_diag"   (GPB_CHAIN_DIAG)   2 = the chain CTA factors diagonal blocks with the 256-thread body              */
 int gpb_set_option(const char* name, int value);
 /* Per-kernel-class device timing: while enabled, each launch group of a class is bracketed
  * by CUDA events on its stream.  Classes: 0 DMMA GEMM, 1 diagonal-block factor, 2 kernel

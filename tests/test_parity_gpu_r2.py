@@ -324,3 +324,67 @@ def test_sharded_posterior_lower_panels_vs_oracle(oracle, n, m, kparams):
 
 def make_k(kparams):
     return GaussianKernel(*kparams) if len(kparams) == 2 else PeriodicKernel(*kparams)
+
+
+# ------------------------------------------------------------------ gp_c host-pointer entry points (C ABI)
+@pytest.mark.parametrize("n,n_p,m", [(16, 2, 9), (150, 3, 70), (300, 2, 33)])
+def test_gp_c_c_abi_vs_oracle_general_inputs(oracle, n, n_p, m):
+    """The five gpb_gp_c_* entry points (reference signatures, host arrays, one library call each) against the
+    oracle's restatement of gp_c.pyx on GENERAL inputs: Ki not symmetric, Kiy not equal to Ki y, arbitrary Kj /
+    Kh -- the formulas must follow the reference's operand order, not properties of kernel matrices."""
+    from gaussian_processes_b200.ext import gp_c
+    rng = np.random.RandomState(100 + n)
+    y = rng.randn(n)
+    Ki = (rng.randn(n, n) * 0.1 + np.eye(n)) / n
+    Kj = rng.randn(n_p, n, n) * 0.3
+    Kh = rng.randn(n_p, n_p, n, n) * 0.2
+    Kiy = rng.randn(n) * 0.5
+    s, lh = 0.7, 0.37
+    d0 = np.empty(n_p + 1)
+    gp_c.dloglh_dtheta(y, Ki, Kj, Kiy, s, d0)
+    assert_parity(d0, oracle.dloglh_reduce(y, Ki, Kj, Kiy, s))
+    d1 = np.empty(n_p + 1)
+    gp_c.dlh_dtheta(y, Ki, Kj, Kiy, s, lh, d1)
+    assert_parity(d1, oracle.dlh_reduce(y, Ki, Kj, Kiy, s, lh))
+    dlh = rng.randn(n_p + 1)
+    d2 = np.empty((n_p + 1, n_p + 1))
+    gp_c.d2lh_dtheta2(y, Ki, Kj, Kh, Kiy, s, lh, dlh, d2)
+    assert_parity(d2, oracle.d2lh_reduce(y, Ki, Kj, Kh, Kiy, s, lh, dlh))
+    Kjxo, Kxox = rng.randn(n_p, m, n), rng.randn(m, n)
+    dm = np.empty((n_p + 1, m))
+    gp_c.dm_dtheta(y, Ki, Kj, Kjxo, Kxox, s, dm)
+    assert_parity(dm, oracle.dm_reduce(y, Ki, Kj, Kjxo, Kxox, s))
+    # log_lh on an SPD K, and the -inf cases
+    A = rng.randn(n, n)
+    K = A @ A.T / n + np.eye(n)
+    assert_parity(gp_c.log_lh(y, K, Kiy), oracle.log_lh_reduce(y, K, Kiy))
+    assert gp_c.log_lh(y, -K, Kiy) == -np.inf                                   # not positive definite
+    assert gp_c.log_lh(y, K * 1e-3 if n >= 150 else K * 1e-30, Kiy) == -np.inf  # log|K| < MIN (gp_c.pyx:22)
+    # argument validation as the Cython declarations do it
+    with pytest.raises(ValueError):
+        gp_c.dloglh_dtheta(y, Ki[:, ::-1], Kj, Kiy, s, d0)
+    with pytest.raises(ValueError):
+        gp_c.dm_dtheta(y, Ki, Kj, Kjxo[:, :-1], Kxox, s, dm)
+
+
+def test_gp_c_c_abi_direct_ctypes():
+    """A caller with no Python package at all: ctypes on libgpb200.so, raw pointers."""
+    import ctypes
+    import os
+    from conftest import ROOT
+    lib = ctypes.CDLL(os.path.join(ROOT, "gaussian_processes_b200", "libgpb200.so"))
+    g = golden("gp_suite_p1")
+    y, Ki, Kj, a = (np.ascontiguousarray(g[k]) for k in ("y", "inv_Kxx", "Kxx_J", "inv_Kxx_y"))
+    n, n_p = y.size, Kj.shape[0]
+    out = np.empty(n_p + 1)
+    vp = ctypes.c_void_p
+    lib.gpb_gp_c_dloglh_dtheta.argtypes = [vp, vp, vp, vp, ctypes.c_double, ctypes.c_int64, ctypes.c_int64, vp]
+    st = lib.gpb_gp_c_dloglh_dtheta(y.ctypes.data, Ki.ctypes.data, Kj.ctypes.data, a.ctypes.data,
+                                    float(g["params"][-1]), n_p, n, out.ctypes.data)
+    assert st == 0
+    assert_parity(out, g["dloglh_dtheta"])
+    llh = ctypes.c_double()
+    lib.gpb_gp_c_log_lh.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)]
+    K = np.ascontiguousarray(g["Kxx"])
+    assert lib.gpb_gp_c_log_lh(y.ctypes.data, K.ctypes.data, a.ctypes.data, n, ctypes.byref(llh)) == 0
+    assert_parity(llh.value, g["log_lh"])
