@@ -102,6 +102,24 @@ class ClockSampler(object):
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def hbm_peak():
+    """(GB/s, source): the driver-measured copy bandwidth when MEASURED_PEAKS.json is present, else the
+    fallback of /opt/skills/guides/B200_PROFILING.md."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json (driver-measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def traffic_from_profiles(batch):
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")))
+        return float(d["dram_bytes_per_gemm_launch_per_candidate"]) * batch
+    except Exception:
+        return None
+
+
 def load_oracle():
     import importlib.util
     spec = importlib.util.spec_from_file_location("gp_oracle", os.path.join(ROOT, "oracle", "gp_oracle.py"))
@@ -278,11 +296,15 @@ def run_ours(args):
         achieved = flops_step / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_nt_tma_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the gemm_nt launches of one step, from
-                # the ncu pass committed as profiles/r01_launches_one_step_b32.csv
-                # (38.76 GB over 73 launches at B=32 -> 16.59 MB per launch per candidate)
-                "traffic": 16.59e6 * B,
-                "traffic_source": "ncu dram bytes, profiles/r01_launches_one_step_b32.csv (per launch, scaled by B/32)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the gemm_nt launches of one step, read from the
+                # summary of the committed ncu pass of the CURRENT code (profiles/ncu_traffic.py writes it);
+                # null when no such summary exists -- never a constant carried over from older code
+                "traffic": traffic_from_profiles(B),
+                "traffic_source": "profiles/r02_gemm_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum per "
+                                  "gemm_nt launch per candidate of one evaluator step (scaled by this run's batch)",
+                "flops_note": "all N^3 algorithmic flop of an evaluation are booked to the GEMM class; the diagonal-block "
+                              "kernel performs (N/128) * 128^3 = N * 128^2 of them (0.1 %% at N=%d)" % n,
+                "hbm_peak_gbs": hbm_peak()[0], "hbm_peak_source": hbm_peak()[1],
                 "algorithmic_flops_per_launch": flops_step / gemm_launches,
                 "avg_launch_ms": gemm_ms / gemm_launches, "launches_per_step": gemm_launches,
                 "peak_source": "measured live: gpb_microbench_fp64 (DMMA.8x8x4 issue rate, 148x8 CTAs); "
@@ -355,8 +377,71 @@ def run_ours(args):
         t_cov = (time.perf_counter() - t0) / 3
         posterior = {"mean_test_pts_per_s": m_mean / t_mean, "cov_test_pts_per_s": m_cov / t_cov,
                      "m_mean": m_mean, "m_cov": m_cov, "n": n,
-                     "note": "public API on a fitted GP (factor + L^-1 cached), host xo in, numpy out "
-                             "(cov includes the D2H of the M x M result)"}
+                     "note": "public API on a fitted GP (factor + L^-1 cached), host xo in, numpy out; the cov figure "
+                             "includes the D2H of the M x M result (134 MB at M=4096) and is PCIe-bound -- the "
+                             "device-only rate is in posterior_sharded.cov_test_pts_per_s_device"}
+
+    # ---- the drop-in property API on ONE GP object at N=4096 (config C2 as a user of gp/gp.py drives it):
+    # cold log_lh, + dloglh_dtheta, + d2lh_dtheta2 after a parameter change (setters drop every cached result)
+    single = None
+    if rank == 0 and not args.no_posterior:
+        gps1 = gpb.GP(gpb.GaussianKernel(1.0, 0.5), x, y, s=1.0)
+        for k in range(3):
+            gps1.set_param("w", 0.5 + 1e-6 * (k + 1)); gps1.log_lh; gps1.dloglh_dtheta; gps1.d2lh_dtheta2
+        torch.cuda.synchronize()
+        ts = np.zeros((8, 3))
+        for k in range(ts.shape[0]):
+            gps1.set_param("w", 0.5 + 1e-5 * (k + 1))
+            t0 = time.perf_counter()
+            l1 = gps1.log_lh
+            ts[k, 0] = time.perf_counter() - t0
+            g1 = gps1.dloglh_dtheta
+            ts[k, 1] = time.perf_counter() - t0
+            h1 = gps1.d2lh_dtheta2
+            ts[k, 2] = time.perf_counter() - t0
+        # the same, gradient asked first (one staged chain: factor + inverse + gradient in one library call)
+        tg = []
+        for k in range(8):
+            gps1.set_param("w", 0.5 - 1e-5 * (k + 1))
+            t0 = time.perf_counter()
+            g1 = gps1.dloglh_dtheta; l1 = gps1.log_lh
+            tg.append(time.perf_counter() - t0)
+        tb = ts.min(axis=0)
+        single = {"workload": "C2 through the drop-in property API: one GP object, N=%d, cold after set_param" % n,
+                  "log_lh_ms": tb[0] * 1e3, "log_lh_plus_dloglh_ms": min(min(tg), tb[1]) * 1e3,
+                  "plus_d2lh_dtheta2_ms": tb[2] * 1e3,
+                  "evals_per_s_log_lh_plus_dloglh": 1.0 / min(min(tg), tb[1]),
+                  "tflops_log_lh_plus_dloglh": float(n) ** 3 / min(min(tg), tb[1]) / 1e12,
+                  "frac_of_dmma_peak": (float(n) ** 3 / min(min(tg), tb[1]) / 1e12 / roof["peak"]) if roof else None,
+                  "note": "host wall time of the property reads (each ends with the read-back of its scalars); "
+                          "the factorisation is the persistent dataflow launch of csrc/chain.cu"}
+
+    # ---- BASELINE config C4: 4096 restarts x N=1024, candidates sharded over the ranks, argmax gather ----
+    c4 = None
+    if not args.no_posterior:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_golden_full import c4_candidates
+        x4, y4 = synth_xy(1024, 0)
+        cand4 = c4_candidates()
+        gp4 = gpb.GP(gpb.GaussianKernel(1.0, 0.5), x4, y4, s=1.0)
+        gp4.fit_MLII(cand4[:256 * world], set_params=False)
+        t4 = []
+        for k in range(3):
+            sync()
+            t0 = time.perf_counter()
+            res4 = gp4.fit_MLII(cand4 * (1.0 + 1e-9 * k), set_params=False)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t4.append(float(tt.item()))
+        c4 = {"workload": "C4: fit_MLII over 4096 candidates x N=1024 (h~U(.5,2), w~U(pi/32,pi/2), s~U(.75,1.5)), "
+                          "candidates sharded over %d GPU(s), all-gather of the [B,8] rows + argmax" % world,
+              "scaling": "strong", "ms": min(t4) * 1e3, "evals_per_s": cand4.shape[0] / min(t4),
+              "tflops": cand4.shape[0] * 1024.0 ** 3 / min(t4) / 1e12, "best_index": int(res4.best_index),
+              "best_log_lh": float(res4.best_log_lh),
+              "note": "public API end to end: host candidates in, argmax + table out (reference best index 4081, "
+                      "log_lh -681.7116082305: tests/golden/full_c4.npz)"}
 
     # ---- BASELINE config C3 on N GPUs: test points sharded over the ranks (strong scaling: M fixed) ----
     sharded = None
@@ -419,6 +504,10 @@ def run_ours(args):
             line["posterior"] = posterior
         if sharded is not None:
             line["posterior_sharded"] = sharded
+        if single is not None:
+            line["single_gp"] = single
+        if c4 is not None:
+            line["c4"] = c4
         if small is not None:
             line["small_gp"] = small
         emit_line(line)
