@@ -42,11 +42,39 @@ __device__ __forceinline__ void load_kparams(KParams* sP, const KParams& byval, 
 // K only (slice 0), the common case (Kxx for the factorisation, K(xo, x), K(xo, xo)): no slice loop, the
 // eight separations of a thread evaluated together.  The generic kernel below spends ~100 issued
 // instructions per element on slice bookkeeping (ncu: FP64 pipe 38 % active); this one ~35.
+// Periodic kernel: sin / cos of the tile's points, once per block (96 sincos for 2048 elements)
+// sin / cos of a difference from the per-point tables, with separately rounded products (no FMA contraction):
+// S(i,j) = -S(j,i) and C(i,j) = C(j,i) hold bit for bit, so K(x, x) stays exactly symmetric like the
+// d = x_i - x_j form it replaces.
+__device__ __forceinline__ double sin_diff(double si, double ci, double sj, double cj) {
+    return __dsub_rn(__dmul_rn(si, cj), __dmul_rn(ci, sj));
+}
+__device__ __forceinline__ double cos_diff(double si, double ci, double sj, double cj) {
+    return __dadd_rn(__dmul_rn(ci, cj), __dmul_rn(si, sj));
+}
+
+template <int KIND>
+__device__ __forceinline__ void stage_sincos(const BuildArgs& a, const KParams& P, double* s_col, double* c_col,
+                                             double* s_row, double* c_row) {
+    if (KIND != GPB_PERIODIC) return;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 64) {
+        const long long j = (long long)blockIdx.x * 64 + tid;
+        sincos((j < a.n2 ? a.x2[j] : 0.0) * P.half_ip, &s_col[tid], &c_col[tid]);
+    } else if (tid < 96) {
+        const long long i = (long long)blockIdx.y * 32 + tid - 64;
+        sincos((i < a.n1 ? a.x1[i] : 0.0) * P.half_ip, &s_row[tid - 64], &c_row[tid - 64]);
+    }
+    __syncthreads();
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) build_k_kernel(const BuildArgs a) {
     __shared__ KParams sP;
+    __shared__ double s_col[64], c_col[64], s_row[32], c_row[32];
     load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
     if (a.lower_only && blockIdx.x > blockIdx.y / 2) return;
+    stage_sincos<KIND>(a, sP, s_col, c_col, s_row, c_row);
     const long long j0 = ((long long)blockIdx.x * 32 + threadIdx.x) * 2;
     if (j0 >= a.cols) return;
     const bool ja = j0 < a.n2, jb = j0 + 1 < a.n2;
@@ -61,7 +89,24 @@ __global__ void __launch_bounds__(256) build_k_kernel(const BuildArgs a) {
         d[2 * r] = xi - xa;
         d[2 * r + 1] = xi - xb;
     }
-    gpb_eval_unique_v<KIND, 8>(sP, d, 1u, u);
+    if (KIND == GPB_PERIODIC) {
+        // K = k0 exp(c1 S^2), S = sin((x_i - x_j) / 2p) = s_i c_j - c_i s_j from the staged tables
+        double arg[8], ev[8];
+        const double sa = s_col[2 * threadIdx.x], ca = c_col[2 * threadIdx.x];
+        const double sb = s_col[2 * threadIdx.x + 1], cb = c_col[2 * threadIdx.x + 1];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const double si = s_row[threadIdx.y + 8 * r], ci = c_row[threadIdx.y + 8 * r];
+            const double S0 = sin_diff(si, ci, sa, ca), S1 = sin_diff(si, ci, sb, cb);
+            arg[2 * r] = sP.c1 * (S0 * S0);
+            arg[2 * r + 1] = sP.c1 * (S1 * S1);
+        }
+        gpb_expv<8>(arg, ev);
+#pragma unroll
+        for (int e = 0; e < 8; e++) u[e][0] = sP.k0 * ev[e];
+    } else {
+        gpb_eval_unique_v<KIND, 8>(sP, d, 1u, u);
+    }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const long long i = i0 + 8 * r;
@@ -83,6 +128,7 @@ __global__ void __launch_bounds__(256) build_k_kernel(const BuildArgs a) {
 template <int KIND, bool VEC2>
 __global__ void __launch_bounds__(256) build_kernel(const BuildArgs a) {
     __shared__ KParams sP;
+    __shared__ double s_col[64], c_col[64], s_row[32], c_row[32];
     load_kparams<KIND>(&sP, a.P, a.Pb, blockIdx.z);
     constexpr int NS = (KIND == GPB_GAUSSIAN) ? 7 : 13;
 
@@ -92,6 +138,7 @@ __global__ void __launch_bounds__(256) build_kernel(const BuildArgs a) {
         if (a.out[s]) need |= 1u << gpb_slice_to_unique(KIND, s);
 
     if (a.lower_only && blockIdx.x > blockIdx.y / 2) return;     // tile strictly above the 64-block diagonal
+    stage_sincos<KIND>(a, sP, s_col, c_col, s_row, c_row);
     const long long j0 = ((long long)blockIdx.x * 32 + threadIdx.x) * 2;
     if (j0 >= a.cols) return;
     const bool two = (j0 + 1 < a.cols);
@@ -108,8 +155,16 @@ __global__ void __launch_bounds__(256) build_kernel(const BuildArgs a) {
         const bool va = vi && (j0 < a.n2), vb = vi && (j0 + 1 < a.n2);
         if (va | vb) {
             const double xi = a.x1[i];
-            gpb_eval_unique<KIND>(sP, xi - xa, need, ua);
-            gpb_eval_unique<KIND>(sP, xi - xb, need, ub);
+            if (KIND == GPB_PERIODIC) {
+                const double si = s_row[threadIdx.y + 8 * r], ci = c_row[threadIdx.y + 8 * r];
+                const double sa = s_col[2 * threadIdx.x], ca = c_col[2 * threadIdx.x];
+                const double sb = s_col[2 * threadIdx.x + 1], cb = c_col[2 * threadIdx.x + 1];
+                gpb_eval_periodic_sc(sP, xi - xa, sin_diff(si, ci, sa, ca), cos_diff(si, ci, sa, ca), need, ua);
+                gpb_eval_periodic_sc(sP, xi - xb, sin_diff(si, ci, sb, cb), cos_diff(si, ci, sb, cb), need, ub);
+            } else {
+                gpb_eval_unique<KIND>(sP, xi - xa, need, ua);
+                gpb_eval_unique<KIND>(sP, xi - xb, need, ub);
+            }
         }
 #pragma unroll
         for (int s = 0; s < NS; s++) {
@@ -245,6 +300,63 @@ __global__ void __launch_bounds__(256) fused_matvec_kernel(const MatvecArgs a) {
 // Posterior-mean fast path (gp.py:597, one pair: slice 0, coefficient 1): the slice is a
 // compile-time constant, a warp owns two rows so every x2 / vector load feeds two kernel
 // evaluations, and lanes take two adjacent columns per 128-bit load.
+// Periodic posterior mean: the block's 16 rows against all columns, the columns' sin / cos staged in
+// shared memory by chunks of MEAN_CH points (one sincos per column per block instead of one per element):
+// S = s_i c_j - c_i s_j, K = k0 exp(c1 S^2).
+#define MEAN_CH 1024
+__global__ void __launch_bounds__(256) mean_periodic_kernel(const MatvecArgs a) {
+    __shared__ KParams sP;
+    __shared__ double s_c[MEAN_CH], c_c[MEAN_CH], v_c[MEAN_CH];
+    load_kparams<GPB_PERIODIC>(&sP, a.P, a.Pb, blockIdx.z);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double* vec = a.vec[0] + (long long)blockIdx.z * a.vstride;
+    double* out = a.out[0] + (long long)blockIdx.z * a.ostride;
+    for (long long g0 = (long long)blockIdx.x * 16; g0 < a.n1; g0 += (long long)gridDim.x * 16) {
+        const long long r0 = g0 + 2 * wid;
+        const bool va = r0 < a.n1, vb = r0 + 1 < a.n1;
+        double sa = 0.0, ca = 1.0, sb = 0.0, cb = 1.0;
+        if (va) sincos(a.x1[r0] * sP.half_ip, &sa, &ca);
+        if (vb) sincos(a.x1[r0 + 1] * sP.half_ip, &sb, &cb);
+        double acc_a = 0.0, acc_b = 0.0;
+        for (long long c0 = 0; c0 < a.n2; c0 += MEAN_CH) {
+            const int nc = (int)((a.n2 - c0 < MEAN_CH) ? a.n2 - c0 : MEAN_CH);
+            __syncthreads();
+            for (int e = threadIdx.x; e < MEAN_CH; e += 256) {
+                double sv = 0.0, cv = 1.0, vv = 0.0;
+                if (e < nc) {
+                    sincos(a.x2[c0 + e] * sP.half_ip, &sv, &cv);
+                    vv = vec[c0 + e];
+                }
+                s_c[e] = sv; c_c[e] = cv; v_c[e] = vv;       // beyond the chunk: weight 0
+            }
+            __syncthreads();
+            // each lane: 4 columns per step for both rows -> 8 independent exponentials
+            for (int e = 4 * lane; e < nc; e += 128) {
+                double arg[8], ev[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double sj = s_c[e + q], cj = c_c[e + q];
+                    const double S0 = sin_diff(sa, ca, sj, cj), S1 = sin_diff(sb, cb, sj, cj);
+                    arg[q] = sP.c1 * (S0 * S0);
+                    arg[4 + q] = sP.c1 * (S1 * S1);
+                }
+                gpb_expv<8>(arg, ev);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    acc_a = fma(ev[q], v_c[e + q], acc_a);
+                    acc_b = fma(ev[4 + q], v_c[e + q], acc_b);
+                }
+            }
+        }
+        acc_a = warp_sum(acc_a) * sP.k0;
+        acc_b = warp_sum(acc_b) * sP.k0;
+        if (lane == 0) {
+            if (va) out[r0] = acc_a;
+            if (vb) out[r0 + 1] = acc_b;
+        }
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) mean_kernel(const MatvecArgs a) {
     __shared__ KParams sP;
@@ -313,7 +425,7 @@ int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int b
         if (nbm > 148 * 16) nbm = 148 * 16;
         const dim3 gm((unsigned)nbm, 1, (unsigned)batch);
         if (kind == GPB_GAUSSIAN) mean_kernel<GPB_GAUSSIAN><<<gm, 256, 0, st>>>(a);
-        else mean_kernel<GPB_PERIODIC><<<gm, 256, 0, st>>>(a);
+        else mean_periodic_kernel<<<gm, 256, 0, st>>>(a);
     } else if (kind == GPB_GAUSSIAN) fused_matvec_kernel<GPB_GAUSSIAN><<<grid, 256, 0, st>>>(a);
     else fused_matvec_kernel<GPB_PERIODIC><<<grid, 256, 0, st>>>(a);
     GPB_LAUNCH_CHECK("fused_matvec_kernel");
