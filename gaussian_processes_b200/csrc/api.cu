@@ -81,7 +81,8 @@ static GpbOption g_options[] = {
     {"gemm_impl", "GPB_GEMM_IMPL", 0, false},
     {"potrf_dataflow", "GPB_POTRF_DATAFLOW", 0, false},
     {"chain_diag", "GPB_CHAIN_DIAG", 0, false},             // 2 = the chain CTA factors diagonal blocks with the 256-thread body
-    {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // CTAs sharing the dataflow factorisation's critical path: 8 (default), 4 or 1     // 0 = one matrix of N <= 8192 by the persistent dataflow launch, 1 = whenever batch == 1, 2 = never         // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
+    {"chain_express", "GPB_CHAIN_EXPRESS", 0, false},       // 1 = six express worker groups for the chain-adjacent tiles (measured: no gain)
+    {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = round-2 v1 group of that many CTAs     // 0 = one matrix of N <= 8192 by the persistent dataflow launch, 1 = whenever batch == 1, 2 = never         // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
 };
 int gpb_get_option(const char* name) {
     for (auto& o : g_options)

@@ -62,6 +62,9 @@ constexpr long long C_TIMEOUT = 4000000000LL;                           // ~2 s 
 
 enum { TASK_TRSM = 0, TASK_UPD = 1 };
 constexpr int g_dclk_off = 2 * 160 * 4;       // phase clocks of one diagonal block behind the worker accounting
+constexpr int g_hclk_off = g_dclk_off + 256;  // helper 0: 8 clock64 stamps per step, then 4 %globaltimer stamps per step
+                                              // (one thread, one store each; read back by gpb_debug_chain_workers for
+                                              //  tests/gpu_potrf_dataflow.py -- the timeline in DESIGN.md comes from these)
 struct ChainTask { unsigned char type, h; short i, j, k; };
 
 struct ChainArgs {
@@ -72,7 +75,8 @@ struct ChainArgs {
     int T; int n_valid;
     int NG;                     // CTAs of the chain group (CTA 0 = the chain, 1..NG-1 its helpers)
     int diag512;                // 1: full diagonal blocks by the 512-thread body (diag_block512.cuh)
-    int* flags;                 // [0] error | DIAG[T] | TP[T] | SP[T] | LRH[2T*T] | CNT[2T*T]
+    int pipelined;              // 1: chain group v2 (c0 publishes every 32-column block; helpers one block behind; inverter CTA)
+    int* flags;                 // [0] error | DIAG[T] | TP[T] | SP[T] | LRH[2T*T] | CNT[2T*T] | LPUB[4T] | XP[4T]
     const ChainTask* bulk; const int* bulk_off;     // per worker group: UPD tasks in (k, j, i, h) order
     const ChainTask* trsm; const int* trsm_off;     // per worker group: TRSM tasks in (k, i, h) order
     long long* clk;             // [T][8] phase clocks of the chain CTA (gpb_debug_chain_clocks)
@@ -85,7 +89,16 @@ __device__ __forceinline__ int* f_tp(const ChainArgs& a, int k) { return a.flags
 __device__ __forceinline__ int* f_sp(const ChainArgs& a, int k) { return a.flags + 1 + 2 * a.T + k; }
 __device__ __forceinline__ int* f_lrh(const ChainArgs& a, int i, int h, int k) { return a.flags + 1 + 3 * a.T + (2 * i + h) * a.T + k; }
 __device__ __forceinline__ int* f_cnt(const ChainArgs& a, int i, int h, int j) { return a.flags + 1 + 3 * a.T + 2 * a.T * a.T + (2 * i + h) * a.T + j; }
-__host__ __device__ inline size_t chain_flag_words(int T) { return 1 + 3 * (size_t)T + 4 * (size_t)T * T; }
+__device__ __forceinline__ int* f_lpub(const ChainArgs& a, int d, int bb) { return a.flags + 1 + 3 * a.T + 4 * a.T * a.T + d * 4 + bb; }
+__device__ __forceinline__ int* f_xp(const ChainArgs& a, int k, int bb) { return a.flags + 1 + 7 * a.T + 4 * a.T * a.T + k * 4 + bb; }
+__device__ __forceinline__ int* f_ux(const ChainArgs& a, int r) { return a.flags + 1 + 11 * a.T + 4 * a.T * a.T + r; }
+__host__ __device__ inline size_t chain_flag_words(int T) { return 1 + 12 * (size_t)T + 4 * (size_t)T * T; }
+
+__device__ __forceinline__ long long gtimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // thread 0 only: spin until *flag >= target; false on time-out or when another CTA raised the error flag
 __device__ __forceinline__ bool spin_ge(const int* flag, int target, int* err) {
@@ -262,6 +275,8 @@ __device__ __forceinline__ void worker_group(const ChainArgs& a, double* ring, v
             if (have_u && lane == 3) { fp = f_lrh(a, u.j, 0, u.k); target = 1; }
             // the first half of a diagonal tile only multiplies by rows 0..63 of L(j,k)
             if (have_u && lane == 4 && !(u.i == u.j && u.h == 0)) { fp = f_lrh(a, u.j, 1, u.k); target = 1; }
+            // (the tile's earlier steps: normally this group's own, but an express group takes over a chain tile)
+            if (have_u && lane == 5) { fp = f_cnt(a, u.i, u.h, u.j); target = u.k; }
             int act = -1;
             const long long t0 = clock64();
             unsigned it = 0;
@@ -269,7 +284,7 @@ __device__ __forceinline__ void worker_group(const ChainArgs& a, double* ring, v
                 const bool ok = fp ? (ld_acquire(fp) >= target) : true;
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (have_r && (m & 3u) == 3u) { act = 0; break; }
-                if (have_u && (m & 28u) == 28u) { act = 1; break; }
+                if (have_u && (m & 60u) == 60u) { act = 1; break; }
                 if ((++it & 63u) == 0) {
                     int stop = 0;
                     if (lane == 0) {
@@ -310,10 +325,12 @@ __device__ __forceinline__ void worker_group(const ChainArgs& a, double* ring, v
 // ===========================================================================
 // rows [r0, r0 + CR) of  X = A(k,k-1) W_{k-1}^T  (in place); X strip also left in shared memory (As)
 template <int CR>
-__device__ __forceinline__ void strip_trsm(const ChainArgs& a, int k, int r0, double* Bs, double* As, int tid) {
+__device__ __forceinline__ void strip_trsm(const ChainArgs& a, int k, int r0, double* Bs, double* As, int tid, int kc = -1) {
+    // tile (k, kc) with the inverted diagonal block kc (kc = k - 1 unless given)
+    if (kc < 0) kc = k - 1;
     const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    double* At = a.A + ((long long)k * CT + r0) * a.ld + (long long)(k - 1) * CT;
-    const double* Wk = a.W + (long long)(k - 1) * CT * a.ldw + (long long)(k - 1) * CT;
+    double* At = a.A + ((long long)k * CT + r0) * a.ld + (long long)kc * CT;
+    const double* Wk = a.W + (long long)kc * CT * a.ldw + (long long)kc * CT;
     // W rows c, columns [0, 32 * (c / 32 + 1)): 16-byte pieces
     for (int e = tid; e < CT * (CT / 2); e += CTHREADS) {
         const int c = e >> 6, p2 = (e & 63) * 2;
@@ -350,9 +367,11 @@ __device__ __forceinline__ void strip_trsm(const ChainArgs& a, int k, int r0, do
 
 // rows [r0, r0 + CR) of  A(k,k) -= X X^T, columns up to the end of the 32-block that holds the diagonal
 template <int CR>
-__device__ __forceinline__ void strip_syrk(const ChainArgs& a, int k, int r0, double* Bs, const double* As, int tid) {
+__device__ __forceinline__ void strip_syrk(const ChainArgs& a, int k, int r0, double* Bs, const double* As, int tid, int kc = -1) {
+    // A(k,k)[strip] -= X[strip] X^T with X = tile (k, kc) (kc = k - 1 unless given)
+    if (kc < 0) kc = k - 1;
     const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const double* Xt = a.A + (long long)k * CT * a.ld + (long long)(k - 1) * CT;
+    const double* Xt = a.A + (long long)k * CT * a.ld + (long long)kc * CT;
     double* Ct = a.A + ((long long)k * CT + r0) * a.ld + (long long)k * CT;
     const int ncol = ((r0 + CR + 31) >> 5) << 5;          // columns (= rows of X) needed
     for (int e = tid; e < ncol * (CT / 2); e += CTHREADS) {
@@ -386,6 +405,44 @@ __device__ __forceinline__ void strip_syrk(const ChainArgs& a, int k, int r0, do
     for (int mi = 0; mi < CR / 8; mi++)
         *reinterpret_cast<double2*>(Ct + (long long)(mi * 8 + g) * a.ld + wid * 8 + 2 * t) =
             make_double2(-acc[mi][0], -acc[mi][1]);
+}
+
+// rows [r0, r0 + CR) of  A(r,j) -= X1 L(j,c)^T  with X1 = this strip of L(r,c) in shared memory (As1); the result
+// also goes to Aout (shared strip): it is the helper's own input of the next pipelined TRSM
+template <int CR>
+__device__ __forceinline__ void strip_upd(const ChainArgs& a, int r, int j, int c, int r0, double* Bs, const double* As1,
+                                          double* Aout, int tid) {
+    const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const double* Lj = a.A + (long long)j * CT * a.ld + (long long)c * CT;
+    double* Ct = a.A + ((long long)r * CT + r0) * a.ld + (long long)j * CT;
+    for (int e = tid; e < CT * (CT / 2); e += CTHREADS) {
+        const int q = e >> 6, p2 = (e & 63) * 2;
+        cp_async16(Bs + q * CSLD + p2, Lj + (long long)q * a.ld + p2);
+    }
+    cp_async_commit();
+    double acc[CR / 8][2];
+#pragma unroll
+    for (int mi = 0; mi < CR / 8; mi++) {
+        const double2 cv = __ldcg(reinterpret_cast<const double2*>(Ct + (long long)(mi * 8 + g) * a.ld + wid * 8 + 2 * t));
+        acc[mi][0] = -cv.x; acc[mi][1] = -cv.y;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const double* ap = As1 + g * CSLD + t;
+    const double* bp = Bs + (wid * 8 + g) * CSLD + t;
+#pragma unroll 4
+    for (int kk = 0; kk < CT / 4; kk++) {
+        const double b = bp[kk * 4];
+#pragma unroll
+        for (int mi = 0; mi < CR / 8; mi++) dmma884(acc[mi][0], acc[mi][1], ap[mi * 8 * CSLD + kk * 4], b);
+    }
+#pragma unroll
+    for (int mi = 0; mi < CR / 8; mi++) {
+        const int rr = mi * 8 + g, cc = wid * 8 + 2 * t;
+        *reinterpret_cast<double2*>(Ct + (long long)rr * a.ld + cc) = make_double2(-acc[mi][0], -acc[mi][1]);
+        Aout[rr * CSLD + cc] = -acc[mi][0];
+        Aout[rr * CSLD + cc + 1] = -acc[mi][1];
+    }
 }
 
 __device__ __forceinline__ void publish(int* flag, int value, int tid) {
@@ -467,11 +524,314 @@ __device__ __forceinline__ void chain_group(const ChainArgs& a, double* csm, vol
     }
 }
 
+// ===========================================================================
+// chain group v2 ("pipelined"): CTA 0 sweeps, CTAs 1..8 helpers, CTA 9 inverter.
+//
+// In v1 the group runs diagonal block (76 k cycles, 22 k of them the 128-level inverse) -> TRSM strips -> SYRK
+// strips one after the other.  Here CTA 0 releases every 32-column block of L_kk (+ its inverted 32x32 diagonal
+// sub-block) as soon as it is final (diag_block512.cuh, lpub), and the helpers run the next tile's TRSM and SYRK
+// block column by block column ONE BLOCK BEHIND the sweeps:
+//     X[:, bb] = (A[:, bb] - sum_{b' < bb} X[:, b'] L(bb,b')^T) W_bb^T          (16-row strip per helper)
+//     C strip  -= X[:, bb] X_all[:, bb]^T                                        (after the group exchanged X[:, bb])
+// so that after the last sweep only the last block column is left.  The 128-level inverse W_kk = L_kk^-1 is only
+// needed by the WORKERS' TRSM tasks (one step of slack): the inverter CTA completes it from global memory and
+// publishes DIAG[k]; CTA 0 goes straight to the next diagonal block.
+// ===========================================================================
+constexpr int NH2 = 8;                  // helpers
+constexpr int CR2 = CT / NH2;           // 16 rows each
+constexpr int XLD = SB + 4;             // stride of 32-column operands (conflict-free fragment loads)
+
+__device__ __forceinline__ void helper_v2(const ChainArgs& a, double* csm, volatile int* s_act, int tid, int h) {
+    int* err = a.flags;
+    const int T = a.T;
+    const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = h * CR2, half = r0 / HR;
+    double* As = csm;                               // [CR2][CSLD]   the strip: A, block column by block column -> X
+    double* As1 = As + CR2 * CSLD;                  // [CR2][CSLD]   urgent phase: this strip of L(k, k-2)
+    double* Bs = As1 + CR2 * CSLD;                  // [CT][CSLD]    urgent phase: second operand (overlays the next three)
+    double* Rs = Bs;                                // [CR2][XLD]    residual of the current block column
+    double* Lk = Rs + CR2 * XLD;                    // 4 blocks [SB][SLD]: L(bb,0..2) and W_bb
+    double* Xa = Lk + 4 * SBSZ;                     // [CT][XLD]     X[:, bb] of the whole tile
+    const int mi = wid & 1, ni = wid >> 1;          // warps 0..7: tile (mi, ni) of a [16 x 32] block
+    const int ncol = ((r0 + CR2 + 31) >> 5) << 5;   // rows of X (= columns of C) this strip needs: lower triangle
+#define HSTAMP(i) do { if (h == 0 && tid == 0) a.wclk[g_hclk_off + k * 8 + (i)] = clock64(); } while (0)
+    for (int k = 1; k < T; k++) {
+        const int d = k - 1;
+        HSTAMP(0);
+        double* At = a.A + ((long long)k * CT + r0) * a.ld + (long long)d * CT;         // strip of tile (k, k-1)
+        const double* Ld = a.A + (long long)d * CT * a.ld + (long long)d * CT;          // diagonal block d
+        const double* Wdg = a.W + (long long)d * CT * a.ldw + (long long)d * CT;
+        double* Ct = a.A + ((long long)k * CT + r0) * a.ld + (long long)k * CT;          // strip of tile (k, k)
+        if (d >= 1) {
+            // ---- urgent phase (while CTA 0 starts diagonal block d): step d-1 of this row's two chain tiles.
+            //      The workers' updates reach these tiles a full step late (inverter -> TRSM -> update, each behind
+            //      whatever task its owner is running), so the group applies the last step itself:
+            //        L(k, d-1) = A(k, d-1) W_{d-1}^T ;  A(k, d) -= L(k, d-1) L(d, d-1)^T ;  A(k, k) -= L(k, d-1) L(k, d-1)^T
+            const int c = d - 1;
+            if (tid == 0) {
+                const bool ok0 = spin_ge(f_diag(a, c), 1, err);
+                if (h == 0) a.wclk[g_hclk_off + 8 * 64 + k * 4 + 0] = gtimer_ns();
+                s_act[0] = (ok0 && spin_ge(f_cnt(a, k, half, c), c, err)) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_act[0]) return;
+            HSTAMP(1);
+            strip_trsm<CR2>(a, k, r0, Bs, As1, tid, c);
+            HSTAMP(2);
+            arrive(f_ux(a, k), NH2, f_lrh(a, k, 0, c), f_lrh(a, k, 1, c), tid);
+            if (tid == 0) s_act[1] = (spin_ge(f_cnt(a, k, half, d), d - 1, err) && spin_ge(f_xp(a, d, 3), NH2, err)) ? 1 : 0;
+            __syncthreads();
+            if (!s_act[1]) return;
+            HSTAMP(3);
+            strip_upd<CR2>(a, k, d, c, r0, Bs, As1, As, tid);
+            HSTAMP(4);
+            if (tid == 0) {
+                const bool ok0 = spin_ge(f_ux(a, k), NH2, err);
+                if (h == 0) a.wclk[g_hclk_off + 8 * 64 + k * 4 + 1] = gtimer_ns();
+                s_act[2] = (ok0 && spin_ge(f_cnt(a, k, half, k), d - 1, err)) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_act[2]) return;
+            HSTAMP(5);
+            strip_syrk<CR2>(a, k, r0, Bs, As1, tid, c);
+            __syncthreads();
+            HSTAMP(6);
+        } else {
+            for (int e = tid; e < CR2 * (CT / 2); e += CTHREADS) {
+                const int r = e >> 6, p2 = (e & 63) * 2;
+                cp_async16(As + r * CSLD + p2, At + (long long)r * a.ld + p2);
+            }
+        }
+        cp_async_commit();
+        double acc[CR2 / 8][2];
+#pragma unroll
+        for (int m = 0; m < CR2 / 8; m++) acc[m][0] = acc[m][1] = 0.0;
+        for (int bb = 0; bb < 4; bb++) {
+            if (tid == 0) s_act[1] = spin_ge(f_lpub(a, d, bb), 1, err) ? 1 : 0;
+            __syncthreads();
+            if (!s_act[1]) return;
+            // L(bb, b') for b' < bb and W_bb -> shared memory
+            for (int e = tid; e < (bb + 1) * SB * (SB / 2); e += CTHREADS) {
+                const int blkq = e / (SB * SB / 2), q = e % (SB * SB / 2), r = q >> 4, c2 = (q & 15) * 2;
+                const double* src = (blkq < bb) ? Ld + (long long)(bb * SB + r) * a.ld + blkq * SB + c2
+                                                : Wdg + (long long)(bb * SB + r) * a.ldw + bb * SB + c2;
+                cp_async16(Lk + (blkq < bb ? blkq : 3) * SBSZ + r * SLD + c2, src);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            if (wid < 8) {
+                // R = A[:, bb] - sum_{b' < bb} X[:, b'] L(bb,b')^T      (tile (mi, ni) of [16 x 32])
+                double r0v = As[(mi * 8 + g) * CSLD + bb * SB + ni * 8 + 2 * t], r1v = As[(mi * 8 + g) * CSLD + bb * SB + ni * 8 + 2 * t + 1];
+                for (int bp = 0; bp < bb; bp++) {
+                    const double* ap = As + (mi * 8 + g) * CSLD + bp * SB + t;
+                    const double* bp_ = Lk + bp * SBSZ + (ni * 8 + g) * SLD + t;
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++) dmma884(r0v, r1v, -ap[kk * 4], bp_[kk * 4]);
+                }
+                Rs[(mi * 8 + g) * XLD + ni * 8 + 2 * t] = r0v;
+                Rs[(mi * 8 + g) * XLD + ni * 8 + 2 * t + 1] = r1v;
+            }
+            __syncthreads();
+            if (wid < 8) {
+                // X[:, bb] = R W_bb^T   (W_bb lower triangular: k <= column)
+                double x0 = 0.0, x1 = 0.0;
+                const double* ap = Rs + (mi * 8 + g) * XLD + t;
+                const double* bp_ = Lk + 3 * SBSZ + (ni * 8 + g) * SLD + t;
+                for (int kk = 0; kk < 2 * ni + 2; kk++) dmma884(x0, x1, ap[kk * 4], bp_[kk * 4]);
+                const int r = mi * 8 + g, c = bb * SB + ni * 8 + 2 * t;
+                *reinterpret_cast<double2*>(At + (long long)r * a.ld + c) = make_double2(x0, x1);
+                As[r * CSLD + c] = x0;
+                As[r * CSLD + c + 1] = x1;
+            }
+            // this strip's X[:, bb] is out: count it; the last arrival of the last block publishes L(k, k-1)
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                const int old = atomicAdd(f_xp(a, k, bb), 1);
+                if (bb == 3 && old == NH2 - 1) {
+                    __threadfence();
+                    st_release(f_lrh(a, k, 0, d), 1);
+                    st_release(f_lrh(a, k, 1, d), 1);
+                }
+                s_act[2] = spin_ge(f_xp(a, k, bb), NH2, err) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_act[2]) return;
+            // X[:, bb] of the rows this strip's part of the lower triangle needs
+            const double* Xt = a.A + (long long)k * CT * a.ld + (long long)d * CT + bb * SB;
+            for (int e = tid; e < ncol * (SB / 2); e += CTHREADS) {
+                const int r = e >> 4, c2 = (e & 15) * 2;
+                cp_async16(Xa + r * XLD + c2, Xt + (long long)r * a.ld + c2);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            if (wid * 8 < ncol) {
+                const double* ap = As + g * CSLD + bb * SB + t;
+                const double* bp_ = Xa + (wid * 8 + g) * XLD + t;
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    const double b = bp_[kk * 4];
+#pragma unroll
+                    for (int m = 0; m < CR2 / 8; m++) dmma884(acc[m][0], acc[m][1], ap[m * 8 * CSLD + kk * 4], b);
+                }
+            }
+            __syncthreads();            // Lk / Xa are reloaded by the next block column
+        }
+        // C strip -= sum_bb X[:, bb] X_all[:, bb]^T   (the tile's earlier steps: workers, then the urgent phase above)
+        if (wid * 8 < ncol) {
+#pragma unroll
+            for (int m = 0; m < CR2 / 8; m++) {
+                double2* p = reinterpret_cast<double2*>(Ct + (long long)(m * 8 + g) * a.ld + wid * 8 + 2 * t);
+                const double2 c = __ldcg(p);
+                *p = make_double2(c.x - acc[m][0], c.y - acc[m][1]);
+            }
+        }
+        arrive(f_sp(a, k), NH2, nullptr, nullptr, tid);
+        HSTAMP(7);
+    }
+#undef HSTAMP
+}
+
+// the 128-level inverse of diagonal block k from its published 32x32 pieces, as early as they arrive:
+//   after block column 1:  W_10 = -W_11 (L_10 W_00)
+//   after block column 2:  S_ij = sum_k L_ik W_kj (i = 2,3; j = 0,1), S_32 = L_32 W_22, W_2j = -W_22 S_2j,
+//                          U_j = S_3j - S_32 S_2j
+//   after block column 3:  W_32 = -W_33 S_32, W_3j = -W_33 U_j      -- ONE phase behind the last 32x32 inverse
+__device__ __forceinline__ void inverter_v2(const ChainArgs& a, double* csm, volatile int* s_act, int tid) {
+    int* err = a.flags;
+    const int T = a.T, wid = tid >> 5;
+    double* Lb = csm;                               // 10 block slots: the six off-diagonal L blocks; the diagonal slots hold W_bb
+    double* Xs = csm + NBLK * SBSZ;                 // S10 W10 S32 S20 S21 S30 S31 U0 U1
+    auto Wdp = [&](int b) { return Lb + blk(b, b) * SBSZ; };
+    double* const S10 = Xs, * const W10 = Xs + SBSZ, * const S32 = Xs + 2 * SBSZ;
+    double* const S20 = Xs + 3 * SBSZ, * const S21 = Xs + 4 * SBSZ, * const S30 = Xs + 5 * SBSZ, * const S31 = Xs + 6 * SBSZ;
+    double* const U0 = Xs + 7 * SBSZ, * const U1 = Xs + 8 * SBSZ;
+    for (int k = 0; k < T; k++) {
+        const long long o = (long long)k * CT;
+        if ((long long)a.n_valid - o < CT) break;                   // identity-padded last block: CTA 0 publishes it itself
+        const double* Ak = a.A + o * a.ld + o;
+        double* Wk = a.W + o * a.ldw + o;
+        double* Vk = a.V ? a.V + o * a.ldv + o : nullptr;
+        auto load_L = [&](int bi, int bj) {
+            for (int e = tid; e < SB * (SB / 2); e += CTHREADS) {
+                const int r = e >> 4, c2 = (e & 15) * 2;
+                cp_async16(Lb + blk(bi, bj) * SBSZ + r * SLD + c2, Ak + (long long)(bi * SB + r) * a.ld + bj * SB + c2);
+            }
+        };
+        auto load_W = [&](int b) {
+            for (int e = tid; e < SB * (SB / 2); e += CTHREADS) {
+                const int r = e >> 4, c2 = (e & 15) * 2;
+                cp_async16(Wdp(b) + r * SLD + c2, Wk + (long long)(b * SB + r) * a.ldw + b * SB + c2);
+            }
+        };
+#pragma unroll 1
+        for (int ph = 0; ph < 5; ph++) {
+            // phases 0,1 after column 1; 2,3 after column 2; 4 after column 3
+            if (ph == 0 || ph == 2 || ph == 4) {
+                const int col = (ph == 0) ? 1 : (ph == 2 ? 2 : 3);
+                if (tid == 0) s_act[0] = spin_ge(f_lpub(a, k, col), 1, err) ? 1 : 0;
+                __syncthreads();
+                if (!s_act[0]) return;
+                if (ph == 0) { load_L(1, 0); load_W(0); load_W(1); }
+                else if (ph == 2) { load_L(2, 0); load_L(2, 1); load_L(3, 0); load_L(3, 1); load_L(3, 2); load_W(2); }
+                else load_W(3);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+            }
+            D512Strip st;
+            bool have = false;
+            if (ph == 0 && wid < 2) {
+                st = d512_prod(Lb + blk(1, 0) * SBSZ, Wdp(0), nullptr, nullptr, 1.0, S10, -1, 0, wid);
+                have = true;
+            } else if (ph == 1 && wid < 2) {
+                st = d512_prod(Wdp(1), S10, nullptr, nullptr, -1.0, W10, 1, 0, wid);
+                have = true;
+            } else if (ph == 2 && wid < 10) {
+                if (wid < 8) {
+                    const int i = 2 + (wid >> 2), j = (wid >> 1) & 1, hf = wid & 1;
+                    double* Sdst = (i == 2) ? (j ? S21 : S20) : (j ? S31 : S30);
+                    st = (j == 0) ? d512_prod(Lb + blk(i, 0) * SBSZ, Wdp(0), Lb + blk(i, 1) * SBSZ, W10, 1.0, Sdst, -1, 0, hf)
+                                  : d512_prod(Lb + blk(i, 1) * SBSZ, Wdp(1), nullptr, nullptr, 1.0, Sdst, -1, 0, hf);
+                } else {
+                    st = d512_prod(Lb + blk(3, 2) * SBSZ, Wdp(2), nullptr, nullptr, 1.0, S32, -1, 0, wid - 8);
+                }
+                have = true;
+            } else if (ph == 3 && wid < 8) {
+                const int j = (wid >> 1) & 1, hf = wid & 1;
+                if (wid < 4) {
+                    st = d512_prod(Wdp(2), j ? S21 : S20, nullptr, nullptr, -1.0, nullptr, 2, j, hf);
+                } else {                                  // U_j = S_3j - S_32 S_2j
+                    st = d512_prod(S32, j ? S21 : S20, nullptr, nullptr, -1.0, j ? U1 : U0, -1, 0, hf);
+                    st.Cin = j ? S31 : S30; st.cin_s = SLD;
+                }
+                have = true;
+            } else if (ph == 4 && wid < 6) {
+                if (wid < 2) st = d512_prod(Wdp(3), S32, nullptr, nullptr, -1.0, nullptr, 3, 2, wid);
+                else st = d512_prod(Wdp(3), ((wid - 2) >> 1) ? U1 : U0, nullptr, nullptr, -1.0, nullptr, 3, (wid - 2) >> 1, wid & 1);
+                have = true;
+            }
+            if (have) d512_strip<8>(st, Wk, a.ldw, Vk, a.ldv);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            __threadfence();
+            st_release(f_diag(a, k), 1);
+            a.wclk[g_hclk_off + 8 * 64 + k * 4 + 2] = gtimer_ns();
+        }
+    }
+}
+
+// CTA 0 of the pipelined group: diagonal blocks only
+__device__ __forceinline__ void chain0_v2(const ChainArgs& a, double* csm, volatile int* s_act, int tid) {
+    int* err = a.flags;
+    const int T = a.T;
+    for (int k = 0; k < T; k++) {
+        CHAIN_STAMP(k, 0);
+        if (k > 0) {
+            if (tid == 0) s_act[0] = spin_ge(f_sp(a, k), NH2, err) ? 1 : 0;
+            __syncthreads();
+            if (!s_act[0]) { if (tid == 0) *a.info = -999; return; }
+        }
+        CHAIN_STAMP(k, 5);
+        const long long o = (long long)k * CT;
+        const long long valid = (long long)a.n_valid - o;
+        const int nsub = valid >= CT ? 4 : (valid <= 0 ? 0 : (int)((valid + SB - 1) / SB));
+        long long* dclk = (k == 1) ? a.wclk + (size_t)g_dclk_off : nullptr;
+        double* Ak = a.A + o * a.ld + o;
+        double* Wk = a.W + o * a.ldw + o;
+        double* Vk = a.V ? a.V + o * a.ldv + o : nullptr;
+        if (nsub == 4) {
+            diag_block_body512<8>(Ak, a.ld, Wk, a.ldw, Vk, a.ldv, a.info, (int)o, csm, dclk, f_lpub(a, k, 0));
+            __syncthreads();
+        } else {
+            if (tid < 256) diag_block_body<true>(Ak, a.ld, Wk, a.ldw, Vk, a.ldv, a.info, (int)o, nsub, csm);
+            __syncthreads();
+            if (tid == 0) {                      // a padded block is the last one: publish everything at once
+                __threadfence();
+                for (int bb = 0; bb < 4; bb++) st_release(f_lpub(a, k, bb), 1);
+                st_release(f_diag(a, k), 1);
+            }
+        }
+        CHAIN_STAMP(k, 6);
+        if (tid == 0) a.wclk[g_hclk_off + 8 * 64 + k * 4 + 3] = gtimer_ns();
+        CHAIN_STAMP(k, 7);
+    }
+}
+
 __global__ void __launch_bounds__(CTHREADS, 1) potrf_dataflow_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) double csm[];
     __shared__ int s_act[4];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < a.NG) {
+        if (a.pipelined) {
+            if (blockIdx.x == 0) chain0_v2(a, csm, s_act, tid);
+            else if ((int)blockIdx.x <= NH2) helper_v2(a, csm, s_act, tid, (int)blockIdx.x - 1);
+            else inverter_v2(a, csm, s_act, tid);
+            return;
+        }
         if (a.NG == 8) chain_group<16>(a, csm, s_act, tid);
         else chain_group<32>(a, csm, s_act, tid);
         return;
@@ -491,10 +851,22 @@ std::map<cudaStream_t, int> g_last_T;
 std::mutex g_plan_mu;
 
 int build_plan(int T, int G, int NG, ChainPlan* out) {
+    const bool pipelined = (NG == NH2 + 2);
+    const bool express = gpb_get_option("chain_express") == 1;
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    auto it = g_plans.find({{T, G}, NG});
+    auto it = g_plans.find({{T, G}, NG + (express ? 100 : 0)});
     if (it != g_plans.end()) { *out = it->second; return GPB_OK; }
     const int nv = 2 * (G - NG);            // worker groups
+    // pipelined group: worker groups 0..3 are EXPRESS groups.  Per step s they run exactly the tasks the chain group
+    // waits for one step later -- TRSM(s+3, s) and the step-s updates of tiles (s+3, s+1), (s+3, s+2), (s+3, s+3) -- and
+    // nothing else, so those tasks never queue behind a regular group's 20-40 k-cycle backlog.
+    // Six express roles, each ALONE on its SM (group 0 of the first six worker CTAs; their group 1 stays empty, so an
+    // express task has the SM's DMMA pipes to itself): TRSM halves | tile (s+3, s+1) halves | tiles (s+3, s+2) then
+    // (s+3, s+3) halves.
+    // Measured (N = 1024 / 2048 / 4096): 0.348 / 0.721 / 1.85 ms with the express groups against 0.345 / 0.694 / 1.81
+    // without -- the helpers' waits only move to the next tile back along the row (every row's TRSM -> update chain
+    // runs at the regular groups' pace before it reaches the express zone) -- so they are OFF unless asked for.
+    const int nexp = (pipelined && express && nv >= 24) ? 12 : 0;
     // Half tile (i,h,j) receives j updates (steps 0..j-1), and at step k exactly the tiles with j > k are
     // live.  Dealing the half tiles out in order of decreasing j (boustrophedon over the groups) therefore
     // balances every live set, i.e. every step of the factorisation, to within one task per group.
@@ -504,22 +876,31 @@ int build_plan(int T, int G, int NG, ChainPlan* out) {
         for (int j = T - 1; j >= 0; j--)
             for (int i = j; i < T; i++)
                 for (int h = 0; h < 2; h++) {
-                    const long long round = n / nv, pos = n % nv;
-                    own[((size_t)2 * i + h) * T + j] = (int)((round & 1) ? nv - 1 - pos : pos);
+                    const int nreg = nv - nexp;
+                    const long long round = n / nreg, pos = n % nreg;
+                    own[((size_t)2 * i + h) * T + j] = nexp + (int)((round & 1) ? nreg - 1 - pos : pos);
                     n++;
                 }
     }
     auto owner = [&](int i, int h, int j) { return own[((size_t)2 * i + h) * T + j]; };
     std::vector<std::vector<ChainTask>> bulk(nv), trsm(nv);
     for (int k = 0; k + 1 < T; k++) {
-        for (int i = k + 2; i < T; i++)
+        // pipelined group: the helpers also run the TRSM of row k+2 and the last worker-side step of the two chain
+        // tiles of every row (their "urgent phase")
+        for (int i = k + (pipelined ? 3 : 2); i < T; i++)
             for (int h = 0; h < 2; h++)
-                trsm[owner(i, h, k)].push_back({TASK_TRSM, (unsigned char)h, (short)i, (short)k, (short)k});
+                trsm[(nexp && i == k + 3) ? 2 * h : owner(i, h, k)].push_back({TASK_TRSM, (unsigned char)h, (short)i, (short)k, (short)k});
         for (int j = k + 1; j < T; j++)
             for (int i = j; i < T; i++) {
                 if (i == k + 1 && j == k + 1) continue;            // the chain group's own update
-                for (int h = 0; h < 2; h++)
-                    bulk[owner(i, h, j)].push_back({TASK_UPD, (unsigned char)h, (short)i, (short)j, (short)k});
+                if (pipelined && ((i == j && k == j - 2) || (i == j + 1 && k == j - 1))) continue;
+                for (int h = 0; h < 2; h++) {
+                    int who = owner(i, h, j);
+                    if (nexp && i == j + 2 && k == j - 1) who = 2 * (2 + h);  // tile (s+3, s+1) at step s: input of the urgent TRSM
+                    if (nexp && i == j + 1 && k == j - 2) who = 2 * (4 + h);  // tile (s+3, s+2) at step s
+                    if (nexp && i == j && k == j - 3) who = 2 * (4 + h);      // tile (s+3, s+3) at step s
+                    bulk[who].push_back({TASK_UPD, (unsigned char)h, (short)i, (short)j, (short)k});
+                }
             }
     }
     auto upload = [&](std::vector<std::vector<ChainTask>>& lists, ChainTask** dt, int** doff) -> int {
@@ -541,7 +922,7 @@ int build_plan(int T, int G, int NG, ChainPlan* out) {
     if (stt) return stt;
     stt = upload(trsm, &p.trsm, &p.trsm_off);
     if (stt) return stt;
-    g_plans[{{T, G}, NG}] = p;
+    g_plans[{{T, G}, NG + (express ? 100 : 0)}] = p;
     *out = p;
     return GPB_OK;
 }
@@ -560,7 +941,7 @@ int chain_init() {
     return GPB_OK;
 }
 
-size_t chain_pool_words(int T) { return (chain_flag_words(T) + 1) / 2 * 2 + (size_t)T * 16 + (size_t)(g_dclk_off + 200) * 2; }
+size_t chain_pool_words(int T) { return (chain_flag_words(T) + 1) / 2 * 2 + (size_t)T * 16 + (size_t)(g_hclk_off + 12 * 64 + 8) * 2; }
 
 }  // namespace
 
@@ -581,8 +962,9 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     if (stt) return stt;
     const int num_sms = g_num_sms;
     const long long nhalf = (long long)T * (T + 1);                // half tiles
-    int NG = gpb_get_option("chain_group");          // CTAs sharing the critical path (4 or 8)
-    if (NG != 4 && NG != 8) NG = 8;
+    int NG = gpb_get_option("chain_group");          // CTAs sharing the critical path: 10 = pipelined (default), 8 or 4 = v1
+    const int pipelined = (NG != 4 && NG != 8) ? 1 : 0;
+    if (pipelined) NG = NH2 + 2;
     GPB_REQUIRE(num_sms >= 2 * NG, "device too small for the dataflow factorisation");
     int G = (int)(((nhalf + 1) / 2 + NG < (long long)num_sms) ? (nhalf + 1) / 2 + NG : num_sms);
     if (G < NG + 1) G = NG + 1;
@@ -613,6 +995,7 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     a.clk = reinterpret_cast<long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2);
     a.wclk = a.clk + (size_t)T * 8;
     a.NG = NG;
+    a.pipelined = pipelined;
     a.diag512 = gpb_get_option("chain_diag");           // 0/1 default body, 2 the 256-thread body, 3.. experiments
     if (a.diag512 == 0) a.diag512 = 1;
     void* args[] = {(void*)&a};
@@ -656,7 +1039,7 @@ extern "C" int gpb_debug_chain_workers(void* stream, long long* out, int max_gro
     int T = 0;
     int stt = chain_debug_pool(stream, &flags, &T);
     if (stt) return stt;
-    if (max_groups > (g_dclk_off + 200) / 4) max_groups = (g_dclk_off + 200) / 4;
+    if (max_groups > (g_hclk_off + 12 * 64) / 4) max_groups = (g_hclk_off + 12 * 64) / 4;
     const long long* clk = reinterpret_cast<const long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2) + (size_t)T * 8;
     GPB_CUDA(cudaMemcpy(out, clk, (size_t)max_groups * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
     return T;
@@ -694,7 +1077,7 @@ extern "C" int gpb_debug_tile_bench(double* A, long long ld, double* W, long lon
     }
     ChainArgs a;
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = nullptr; a.ldv = 0; a.info = nullptr; a.T = 3; a.n_valid = 0;
-    a.NG = 8; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
+    a.NG = 8; a.pipelined = 0; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
     a.clk = nullptr; a.wclk = nullptr;
     chain_tile_bench_kernel<<<grid, CTHREADS, C_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(a, reps, mode, out_dev);
     GPB_LAUNCH_CHECK("chain_tile_bench_kernel");

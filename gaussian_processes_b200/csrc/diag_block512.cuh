@@ -128,7 +128,11 @@ __device__ __forceinline__ D512Strip d512_prod(const double* A1, const double* B
 template <int KKU>
 __device__ __forceinline__ void diag_block_body512(double* A, long long ld, double* W, long long ldw, double* V,
                                                    long long ldv, int* info, int col0, double* sm,
-                                                   long long* dclk = nullptr) {
+                                                   long long* dclk = nullptr, int* lpub = nullptr) {
+    // lpub != nullptr (pipelined chain group, chain.cu): after each 32-column step the block column of L and the
+    // inverted 32x32 diagonal sub-block go to global memory at once and lpub[bb] is released -- the helper CTAs run
+    // the next tile's TRSM / SYRK one 32-column block behind the sweeps -- and the 128-level inverse (everything
+    // after the last 32x32 inverse) is left to the group's inverter CTA.
 #define D512_STAMP(i) do { if (dclk && threadIdx.x == 0) dclk[i] = clock64(); } while (0)
     D512_STAMP(0);
     double* Lb = sm;                          // 10 lower sub-blocks (off-diagonal: stride SLD, diagonal: DLD)
@@ -192,8 +196,9 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
     //   7           S(4)    no sweep: inverse of L_33, L column 3 out, S_32, S_2j, S_3j
     //   8           T2      W_32, W_2j, inverted diagonal blocks out
     //   9           T3      W_3j
+    const int nph = lpub ? 8 : 10;
 #pragma unroll 1
-    for (int ph = 0; ph < 10; ph++) {
+    for (int ph = 0; ph < nph; ph++) {
         if (dclk && ph == 3 && tid == 0) dclk[25] = clock64();
         const bool is_s = (ph <= 7) && ((ph & 1) == 0 || ph == 7);
         const int bb = (ph <= 6) ? (ph >> 1) : 4;               // S / C index (S(4) = the inverse-only phase)
@@ -312,9 +317,21 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                     double* Wo = Wd + (bb - 1) * SBSZ;
 #pragma unroll
                     for (int r = 0; r < SB; r++) Wo[r * SLD + lane] = w[r];
+                    if (lpub) {
+                        __syncwarp();
+                        store_Wdiag(bb - 1, lane, 32);
+                        asm volatile("bar.sync 6, 96;\n" ::: "memory");      // warps 6, 7: the L column is out
+                        if (lane == 0) {
+                            __threadfence();
+                            st_release(lpub + (bb - 1), 1);
+                        }
+                    }
                 }
             } else if (wid == 6 || wid == 7) {
-                if (bb > 0) store_Lcol(bb - 1, tid - 6 * 32, 64);      // previous L column -> global
+                if (bb > 0) {
+                    store_Lcol(bb - 1, tid - 6 * 32, 64);              // previous L column -> global
+                    if (lpub) asm volatile("bar.sync 6, 96;\n" ::: "memory");
+                }
             } else if (wid >= 9 && (wid & 3) != 0) {
                 // (warps 4, 8, 12 share the sweep's sub-partition and stay idle while it runs)
                 const int slot = wid - 9 - (wid > 12);                  // warps 9 10 11 13 14 15 -> 0..5
@@ -334,7 +351,7 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                     // cache for C(0) (the sweep streams 36 KB of straight-line code through the 32 KB cache)
                     st0 = d512_prod(S20, S21, nullptr, nullptr, 0.0, S30, -1, 0, 0);
                     nst = 1;
-                } else if (bb == 3 && slot < 2) {
+                } else if (bb == 3 && slot < 2 && !lpub) {
                     // ---- first level of the 128-level inverse, left half: W_10 = -W_11 (L_10 W_00)
                     st0 = d512_prod(Lb + blk(1, 0) * SBSZ, Wd, nullptr, nullptr, 1.0, S10, -1, 0, slot);
                     st1 = d512_prod(Wd + SBSZ, S10, nullptr, nullptr, -1.0, W10, 1, 0, slot);
@@ -342,7 +359,7 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                     pair_sync = true;
                 }
             }
-            if (bb == 4) {
+            if (bb == 4 && !lpub) {
                 // S(4): S_32 = L_32 W_22 (warps 9, 10) and S_ij = sum_k L_ik W_kj, i = 2,3; j = 0,1 (eight strips)
                 int item = -1;
                 if (wid == 9 || wid == 10) {

@@ -8,10 +8,12 @@ import torch
 from gaussian_processes_b200 import _lib, engine, device as D
 from conftest import synth_xy
 
-sizes = [int(a) for a in sys.argv[1:] if not a.startswith("d")] or [256, 384, 1024, 2048, 4096, 8192]
+sizes = [int(a) for a in sys.argv[1:] if not a.startswith(("d", "g"))] or [256, 384, 1024, 2048, 4096, 8192]
 for a in sys.argv[1:]:
     if a.startswith("d"):
         _lib.set_option("chain_diag", int(a[1:]))
+    if a.startswith("g"):
+        _lib.set_option("chain_group", int(a[1:]))
 for nn in sizes:
     xx, yy = synth_xy(nn, 0)
     eng = engine.Engine(engine.GAUSSIAN, (1.0, 0.5), 1.0, xx, yy)
@@ -58,8 +60,9 @@ d = np.diff(c, axis=1)[1:]
 names = ["wait_sub", "trsm", "publish", "wait_diag", "syrk", "diag", "publish2"]
 print("chain phases (cycles, mean over steps 1..):", {n: int(v) for n, v in zip(names, d.mean(axis=0))})
 print("chain phases (cycles, step 1, mid, last):", d[0].tolist(), d[len(d) // 2].tolist(), d[-1].tolist())
-print("step total mean cycles", int((c[1:, 7] - c[1:, 0]).mean()), "whole", int(c[-1, 7] - c[0, 0]))
-nc = 296 + 24 + 50        # 2 * 148 worker-group rows + the diagonal block's phase clocks at [320, 324)
+print("step total mean cycles", int((c[1:, 7] - c[1:, 0]).mean()), "whole", int(c[-1, 7] - c[0, 0]),
+      "| pipelined group: wait for the diagonal tile %d, diagonal block %d" % ((c[1:, 5] - c[1:, 0]).mean(), (c[1:, 6] - c[1:, 5]).mean()))
+nc = (1280 + 256 + 12 * 64) // 4        # 2 * 148 worker-group rows + the diagonal block's phase clocks at [320, 324)
 wb = (ctypes.c_longlong * (nc * 4))()
 _lib.lib.gpb_debug_chain_workers.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 _lib.lib.gpb_debug_chain_workers(D.stream_ptr(), wb, nc)
@@ -69,6 +72,13 @@ arr = w[328:368].reshape(-1)[:160].reshape(10, 16) - dc[0]
 names = ["S0", "C0", "S1", "C1", "S2", "C2", "S3", "T1", "T2", "T3"]
 for ph in range(10):
     print("  %s warp arrivals (cycles since block start):" % names[ph], arr[ph].tolist())
+hc = w[(1280 + 256) // 4:(1280 + 256 + 8 * T) // 4].reshape(-1)[:8 * T].reshape(T, 8)
+kk = min(T - 2, max(2, T // 2))
+print("helper 0 at step %d (cycles rel. to the chain CTA's step start): start %d | urgent: inputs ready %d, trsm done %d, upd inputs ready %d, upd done %d, syrk inputs ready %d, syrk done %d | end %d || chain CTA: tile ready %d, diag done %d" % (
+    (kk,) + tuple((hc[kk, :8] - c[kk - 1, 0]).tolist()) + (c[kk - 1, 5] - c[kk - 1, 0], c[kk - 1, 6] - c[kk - 1, 0])))
+h2 = w[(1280 + 256 + 8 * 64) // 4:(1280 + 256 + 12 * 64) // 4].reshape(-1)[:4 * T].reshape(T, 4)
+print("   (global timer, ns) inverter: DIAG[k] published after the chain CTA finished diagonal block k:", (h2[1:T - 1, 2] - h2[1:T - 1, 3]).tolist())
+print("   (global timer, ns) helper 0 iteration k: DIAG[k-2] seen after the chain CTA finished block k-2:", (h2[3:T, 0] - h2[1:T - 2, 3]).tolist())
 w = w[:296]
 w = w[w[:, 3] > 0]
 print("worker groups: n=%d tasks/group mean %.1f max %d | cycles mean: wait %d trsm %d upd %d | per half-tile task busy %d | busiest group total %d, least busy %d" % (
