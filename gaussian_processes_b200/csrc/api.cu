@@ -78,11 +78,11 @@ static GpbOption g_options[] = {
     {"potrf_inner", "GPB_POTRF_INNER", 0, false},     // 128-columns per outer Cholesky panel
     {"potrf_lookahead", "GPB_POTRF_LOOKAHEAD", 0, false},   // 0 = panel look-ahead for one matrix of N >= 6144, 1 = always, 2 = off
     {"potrf_panel_rl", "GPB_POTRF_PANEL_RL", 0, false},     // 0 = right-looking panel steps for one matrix, 1 = always, 2 = never
-    {"gemm_impl", "GPB_GEMM_IMPL", 0, false},
-    {"potrf_dataflow", "GPB_POTRF_DATAFLOW", 0, false},
+    {"gemm_impl", "GPB_GEMM_IMPL", 0, false},               // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
+    {"potrf_dataflow", "GPB_POTRF_DATAFLOW", 0, false},     // 0 = one matrix of 256 <= N <= 6144 by the persistent dataflow launch, 1 = whenever batch == 1, 2 = never
     {"chain_diag", "GPB_CHAIN_DIAG", 0, false},             // 2 = the chain CTA factors diagonal blocks with the 256-thread body
     {"chain_express", "GPB_CHAIN_EXPRESS", 0, false},       // 1 = six express worker groups for the chain-adjacent tiles (measured: no gain)
-    {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = round-2 v1 group of that many CTAs     // 0 = one matrix of N <= 8192 by the persistent dataflow launch, 1 = whenever batch == 1, 2 = never         // 0 = TMA + mbarrier pipeline, 1 = cp.async pipeline
+    {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = the first chain group of that many CTAs
 };
 int gpb_get_option(const char* name) {
     for (auto& o : g_options)
