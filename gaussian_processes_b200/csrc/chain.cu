@@ -34,6 +34,7 @@
 // memory, never through L1: tiles are produced by other SMs).  The warp -> (row, column) block map pairs column
 // blocks (0,3), (1,2) on each SM sub-partition: triangular skipping (TRSM: k <= column) then shortens every
 // sub-partition's DMMA queue alike.
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -66,6 +67,10 @@ constexpr int g_hclk_off = g_dclk_off + 256;  // helper 0: 8 clock64 stamps per 
                                               // (one thread, one store each; read back by gpb_debug_chain_workers for
                                               //  tests/gpu_potrf_dataflow.py -- the timeline in DESIGN.md comes from these)
 struct ChainTask { unsigned char type, h; short i, j, k; };
+// One half tile owned by a worker group (scheduler 0): it receives the updates of steps 0..nupd-1 from its owner,
+// then (has_trsm) the owner's TRSM at step j.  (The last one or two steps of the tiles next to the diagonal belong to
+// the chain group.)
+struct ChainTile { short i, j; unsigned char h, nupd, has_trsm, pad; };
 
 struct ChainArgs {
     double* A; long long ld;
@@ -79,6 +84,7 @@ struct ChainArgs {
     int* flags;                 // [0] error | DIAG[T] | TP[T] | SP[T] | LRH[2T*T] | CNT[2T*T] | LPUB[4T] | XP[4T]
     const ChainTask* bulk; const int* bulk_off;     // per worker group: UPD tasks in (k, j, i, h) order
     const ChainTask* trsm; const int* trsm_off;     // per worker group: TRSM tasks in (k, i, h) order
+    const ChainTile* tiles; const int* tile_off;    // per worker group: owned half tiles in (j, i, h) order (<= 32), or null
     long long* clk;             // [T][8] phase clocks of the chain CTA (gpb_debug_chain_clocks)
     long long* wclk;            // [2 * grid][4] per worker group: cycles waiting | in TRSM | in UPD | tasks
 };
@@ -310,6 +316,94 @@ __device__ __forceinline__ void worker_group(const ChainArgs& a, double* ring, v
             const ChainTask u = a.bulk[bt++];
             task_upd(a, u.i, u.h, u.j, u.k, ring, ltid, grp);
             publish_group(f_cnt(a, u.i, u.h, u.j), u.k + 1, ltid, grp);
+            w_upd += clock64() - tw1;
+        }
+        w_n++;
+    }
+    if (ltid == 0) {
+        a.wclk[v * 4 + 0] = w_wait; a.wclk[v * 4 + 1] = w_trsm;
+        a.wclk[v * 4 + 2] = w_upd; a.wclk[v * 4 + 3] = w_n;
+    }
+}
+
+
+// Scheduler 0 ("most urgent runnable tile first").  A group owns at most 32 half tiles; lane t of its first warp keeps
+// tile t's progress (the next step to apply) in a register and polls that tile's next task -- the update of step `next`
+// (L(i,next) and L(j,next) final) or, after the last update, the TRSM (DIAG[j]) -- so ONE round of acquire loads covers
+// every task the group could run.  Tiles are sorted by column: the lowest runnable lane is the task whose result is
+// needed first (column j is consumed at step j).  With the in-order lists of scheduler 1 the step-s update of the tile
+// NEXT to the current column -- the only thing between TRSM(i,s) and TRSM(i,s+1) on row i's serial chain -- queued
+// behind the group's backlog of far-off tiles from step s-1.
+// No deadlock: a group never waits while one of its tasks is runnable, and the globally earliest unfinished task
+// (in step order) always is.
+__device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* ring, volatile int* s_act, volatile int* s_task,
+                                                 int ltid, int grp) {
+    int* err = a.flags;
+    const int v = ((int)blockIdx.x - a.NG) * 2 + grp;          // worker group index
+    const int t0 = a.tile_off[v], nt = a.tile_off[v + 1] - t0;
+    ChainTile my = {0, 0, 0, 0, 0, 0};
+    int next = 0;
+    bool live = false;
+    if (ltid < 32 && ltid < nt) {
+        my = a.tiles[t0 + ltid];
+        live = (my.nupd > 0) || my.has_trsm;
+    }
+    long long w_wait = 0, w_trsm = 0, w_upd = 0, w_n = 0;
+    for (;;) {
+        const long long tw0 = clock64();
+        if (ltid < 32) {
+            const int lane = ltid;
+            const long long tp0 = clock64();
+            unsigned it = 0;
+            int act = -1;
+            for (;;) {
+                bool ok = false;
+                if (live) {
+                    if (next < (int)my.nupd) {
+                        ok = ld_acquire(f_lrh(a, my.i, my.h, next)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next)) >= 1 &&
+                             ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next)) >= 1);
+                    } else {
+                        ok = ld_acquire(f_diag(a, my.j)) >= 1;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const unsigned lv = __ballot_sync(0xffffffffu, live);
+                if (lv == 0u) { act = -2; break; }
+                if (m) { act = __ffs(m) - 1; break; }
+                if ((++it & 63u) == 0) {
+                    int stop = 0;
+                    if (lane == 0) {
+                        if (ld_acquire(err) != 0) stop = 1;
+                        else if (clock64() - tp0 > C_TIMEOUT) { atomicExch(err, 3); stop = 1; }
+                    }
+                    if (__shfl_sync(0xffffffffu, stop, 0)) break;
+                }
+            }
+            if (act >= 0 && lane == act) {
+                const bool is_upd = next < (int)my.nupd;
+                s_task[grp * 4 + 0] = is_upd ? TASK_UPD : TASK_TRSM;
+                s_task[grp * 4 + 1] = ((int)my.i << 16) | (int)my.j;
+                s_task[grp * 4 + 2] = (int)my.h;
+                s_task[grp * 4 + 3] = is_upd ? next : (int)my.j;
+                next++;
+                live = is_upd ? (next < (int)my.nupd || my.has_trsm) : false;
+            }
+            if (lane == 0) s_act[grp] = act;
+        }
+        group_bar(grp);
+        const int act = s_act[grp];
+        if (act < 0) break;
+        const int type = s_task[grp * 4 + 0], ij = s_task[grp * 4 + 1], h = s_task[grp * 4 + 2], k = s_task[grp * 4 + 3];
+        const int i = ij >> 16, j = ij & 0xffff;
+        const long long tw1 = clock64();
+        w_wait += tw1 - tw0;
+        if (type == TASK_TRSM) {
+            task_trsm(a, i, h, k, ring, ltid, grp);
+            publish_group(f_lrh(a, i, h, k), 1, ltid, grp);
+            w_trsm += clock64() - tw1;
+        } else {
+            task_upd(a, i, h, j, k, ring, ltid, grp);
+            publish_group(f_cnt(a, i, h, j), k + 1, ltid, grp);
             w_upd += clock64() - tw1;
         }
         w_n++;
@@ -824,6 +918,7 @@ __device__ __forceinline__ void chain0_v2(const ChainArgs& a, double* csm, volat
 __global__ void __launch_bounds__(CTHREADS, 1) potrf_dataflow_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) double csm[];
     __shared__ int s_act[4];
+    __shared__ int s_task[8];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < a.NG) {
         if (a.pipelined) {
@@ -837,13 +932,15 @@ __global__ void __launch_bounds__(CTHREADS, 1) potrf_dataflow_kernel(const Chain
         return;
     }
     const int grp = tid >> 8;
-    worker_group(a, csm + grp * G_RING, s_act, tid & 255, grp);
+    if (a.tiles) worker_group_edf(a, csm + grp * G_RING, s_act, s_task, tid & 255, grp);
+    else worker_group(a, csm + grp * G_RING, s_act, tid & 255, grp);
 }
 
 // ---- host side: task lists per (T, grid, NG) ------------------------------------------------------------
 struct ChainPlan {
     ChainTask* bulk = nullptr; int* bulk_off = nullptr;
     ChainTask* trsm = nullptr; int* trsm_off = nullptr;
+    ChainTile* tiles = nullptr; int* tile_off = nullptr;    // null when a group would own more than 32 half tiles
 };
 std::map<std::pair<std::pair<int, int>, int>, ChainPlan> g_plans;
 std::map<cudaStream_t, std::pair<int*, size_t>> g_flag_pool;
@@ -922,6 +1019,52 @@ int build_plan(int T, int G, int NG, ChainPlan* out) {
     if (stt) return stt;
     stt = upload(trsm, &p.trsm, &p.trsm_off);
     if (stt) return stt;
+    // scheduler 0: the same ownership as tile lists, most urgent (lowest column) first
+    if (!nexp) {
+        std::vector<ChainTile> flat;
+        std::vector<int> off(nv + 1, 0);
+        std::vector<std::vector<ChainTile>> tl(nv);
+        size_t most = 0;
+        // a tile's deadline = the step that consumes its last worker-side update: column j for most, one or two
+        // steps earlier for the tiles the chain group finishes itself
+        std::vector<std::pair<std::pair<int, int>, std::pair<int, int>>> order;       // ((deadline, j), (i, h))
+        for (int j = 0; j < T; j++)
+            for (int i = j; i < T; i++)
+                for (int h = 0; h < 2; h++) {
+                    int dl = j;
+                    if (pipelined) dl = j - (i == j ? 2 : (i == j + 1 ? 1 : 0));
+                    else dl = j - (i == j ? 1 : 0);
+                    order.push_back({{dl, j}, {i, h}});
+                }
+        std::sort(order.begin(), order.end());
+        for (auto& o : order) {
+            const int j = o.first.second, i = o.second.first, h = o.second.second;
+            int nupd = j, has_trsm;
+            if (pipelined) {
+                has_trsm = i >= j + 3;
+                if (i == j) nupd = j - 2;           // steps j-2 (urgent phase) and j-1 (pipelined columns) are the helpers'
+                if (i == j + 1) nupd = j - 1;       // step j-1 is the helpers' urgent phase
+            } else {
+                has_trsm = i >= j + 2;
+                if (i == j) nupd = j - 1;
+            }
+            if (nupd < 0) nupd = 0;
+            auto& l = tl[owner(i, h, j)];
+            l.push_back({(short)i, (short)j, (unsigned char)h, (unsigned char)nupd, (unsigned char)has_trsm, 0});
+            if (l.size() > most) most = l.size();
+        }
+        if (most <= 32) {
+            for (int g = 0; g < nv; g++) {
+                off[g] = (int)flat.size();
+                flat.insert(flat.end(), tl[g].begin(), tl[g].end());
+            }
+            off[nv] = (int)flat.size();
+            GPB_CUDA(cudaMalloc(&p.tiles, (flat.size() + 1) * sizeof(ChainTile)));
+            GPB_CUDA(cudaMalloc(&p.tile_off, (nv + 1) * sizeof(int)));
+            GPB_CUDA(cudaMemcpy(p.tiles, flat.data(), flat.size() * sizeof(ChainTile), cudaMemcpyHostToDevice));
+            GPB_CUDA(cudaMemcpy(p.tile_off, off.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        }
+    }
     g_plans[{{T, G}, NG + (express ? 100 : 0)}] = p;
     *out = p;
     return GPB_OK;
@@ -992,6 +1135,8 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = V; a.ldv = ldv; a.info = info;
     a.T = T; a.n_valid = (int)n_valid; a.flags = flags;
     a.bulk = plan.bulk; a.bulk_off = plan.bulk_off; a.trsm = plan.trsm; a.trsm_off = plan.trsm_off;
+    const bool lists = gpb_get_option("chain_sched") == 1;       // 1 = in-order task lists, 0 = most urgent runnable tile first
+    a.tiles = lists ? nullptr : plan.tiles; a.tile_off = lists ? nullptr : plan.tile_off;
     a.clk = reinterpret_cast<long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2);
     a.wclk = a.clk + (size_t)T * 8;
     a.NG = NG;
@@ -1076,6 +1221,7 @@ extern "C" int gpb_debug_tile_bench(double* A, long long ld, double* W, long lon
         attr_set = true;
     }
     ChainArgs a;
+    a.tiles = nullptr; a.tile_off = nullptr;
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = nullptr; a.ldv = 0; a.info = nullptr; a.T = 3; a.n_valid = 0;
     a.NG = 8; a.pipelined = 0; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
     a.clk = nullptr; a.wclk = nullptr;

@@ -8,12 +8,16 @@ import torch
 from gaussian_processes_b200 import _lib, engine, device as D
 from conftest import synth_xy
 
-sizes = [int(a) for a in sys.argv[1:] if not a.startswith(("d", "g"))] or [256, 384, 1024, 2048, 4096, 8192]
+sizes = [int(a) for a in sys.argv[1:] if not a.startswith(("d", "g", "s", "e"))] or [256, 384, 1024, 2048, 4096, 8192]
 for a in sys.argv[1:]:
     if a.startswith("d"):
         _lib.set_option("chain_diag", int(a[1:]))
     if a.startswith("g"):
         _lib.set_option("chain_group", int(a[1:]))
+    if a.startswith("s"):
+        _lib.set_option("chain_sched", int(a[1:]))
+    if a.startswith("e"):
+        _lib.set_option("chain_express", int(a[1:]))
 for nn in sizes:
     xx, yy = synth_xy(nn, 0)
     eng = engine.Engine(engine.GAUSSIAN, (1.0, 0.5), 1.0, xx, yy)
