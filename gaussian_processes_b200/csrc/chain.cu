@@ -61,7 +61,9 @@ constexpr int C_SMEM_1 = (C_SMEM_0 > C_STRIP_MAX) ? C_SMEM_0 : C_STRIP_MAX;
 constexpr int C_SMEM = (C_SMEM_1 > DIAG512_SMEM) ? C_SMEM_1 : DIAG512_SMEM;
 constexpr long long C_TIMEOUT = 4000000000LL;                           // ~2 s of SM clocks
 
-enum { TASK_TRSM = 0, TASK_UPD = 1 };
+enum { TASK_TRSM = 0, TASK_UPD = 1, TASK_MUPD = 2 };
+constexpr int NH2 = 8;                  // helpers of the pipelined chain group
+constexpr int C_COMPLETE = 1 << 20;     // CNT value of a half tile that has received all its worker-side updates
 constexpr int g_dclk_off = 2 * 160 * 4;       // phase clocks of one diagonal block behind the worker accounting
 constexpr int g_hclk_off = g_dclk_off + 256;  // helper 0: 8 clock64 stamps per step, then 4 %globaltimer stamps per step
                                               // (one thread, one store each; read back by gpb_debug_chain_workers for
@@ -70,7 +72,7 @@ struct ChainTask { unsigned char type, h; short i, j, k; };
 // One half tile owned by a worker group (scheduler 0): it receives the updates of steps 0..nupd-1 from its owner,
 // then (has_trsm) the owner's TRSM at step j.  (The last one or two steps of the tiles next to the diagonal belong to
 // the chain group.)
-struct ChainTile { short i, j; unsigned char h, nupd, has_trsm, pad; };
+struct ChainTile { short i, j; unsigned char h, nupd, has_trsm, has_m; short dl, pad; };    // dl: step that consumes the finished tile
 
 struct ChainArgs {
     double* A; long long ld;
@@ -81,7 +83,10 @@ struct ChainArgs {
     int NG;                     // CTAs of the chain group (CTA 0 = the chain, 1..NG-1 its helpers)
     int diag512;                // 1: full diagonal blocks by the 512-thread body (diag_block512.cuh)
     int pipelined;              // 1: chain group v2 (c0 publishes every 32-column block; helpers one block behind; inverter CTA)
-    int* flags;                 // [0] error | DIAG[T] | TP[T] | SP[T] | LRH[2T*T] | CNT[2T*T] | LPUB[4T] | XP[4T]
+    int mform;                  // 1: last worker update of a tile in M form, worker TRSMs out of place (see worker_group_edf)
+    long long* tclk;            // trace (%globaltimer): [2T][T][4] per half tile: last update start | complete | TRSM start | done; then [T][4]
+    double* M;                  // [3][T] tiles [128][128]: M_{k+c,k} = L(k+c,k) W_k  (c = 1..3)
+    int* flags;                 // [0] error | DIAG[T] | TP[T] | SP[T] | LRH[2T*T] | CNT[2T*T] | LPUB[4T] | XP[4T] | UX[T] | MP[3T]
     const ChainTask* bulk; const int* bulk_off;     // per worker group: UPD tasks in (k, j, i, h) order
     const ChainTask* trsm; const int* trsm_off;     // per worker group: TRSM tasks in (k, i, h) order
     const ChainTile* tiles; const int* tile_off;    // per worker group: owned half tiles in (j, i, h) order (<= 32), or null
@@ -98,7 +103,16 @@ __device__ __forceinline__ int* f_cnt(const ChainArgs& a, int i, int h, int j) {
 __device__ __forceinline__ int* f_lpub(const ChainArgs& a, int d, int bb) { return a.flags + 1 + 3 * a.T + 4 * a.T * a.T + d * 4 + bb; }
 __device__ __forceinline__ int* f_xp(const ChainArgs& a, int k, int bb) { return a.flags + 1 + 7 * a.T + 4 * a.T * a.T + k * 4 + bb; }
 __device__ __forceinline__ int* f_ux(const ChainArgs& a, int r) { return a.flags + 1 + 11 * a.T + 4 * a.T * a.T + r; }
-__host__ __device__ inline size_t chain_flag_words(int T) { return 1 + 12 * (size_t)T + 4 * (size_t)T * T; }
+__device__ __forceinline__ int* f_mp(const ChainArgs& a, int c, int k) { return a.flags + 1 + 12 * a.T + 4 * a.T * a.T + (c - 1) * a.T + k; }
+__host__ __device__ inline size_t chain_flag_words(int T) { return 1 + 15 * (size_t)T + 4 * (size_t)T * T; }
+__device__ __forceinline__ double* m_tile(const ChainArgs& a, int c, int k) { return a.M + ((long long)(c - 1) * a.T + k) * (CT * CT); }
+// where L(i,k) lives while the factorisation runs: worker TRSMs (i >= k + 3) write to the unused strictly-lower tile (i,k)
+// of W in M-form mode (the tile of A keeps A'(i,k) for the M-form readers and is overwritten at the very end)
+__device__ __forceinline__ const double* l_tile(const ChainArgs& a, int i, int k, long long& ld) {
+    if (a.mform && i >= k + 3) { ld = a.ldw; return a.W + (long long)i * CT * a.ldw + (long long)k * CT; }
+    ld = a.ld;
+    return a.A + (long long)i * CT * a.ld + (long long)k * CT;
+}
 
 __device__ __forceinline__ long long gtimer_ns() {
     long long t;
@@ -201,23 +215,35 @@ __device__ __forceinline__ void task_trsm(const ChainArgs& a, int i, int h, int 
         for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     half_mm(acc, At, a.ld, Wk, a.ldw, wm, wn, (wn + 1) * 2, ring, ltid, grp);
     // every thread's loads of the half tile are complete (barrier at the end of half_mm): safe to overwrite
+    long long ldd;
+    double* Dt = const_cast<double*>(l_tile(a, i, k, ldd)) + (long long)h * HR * ldd;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) {
-            double* dst = At + (long long)(wm * 32 + mi * 8 + g) * a.ld + wn * 32 + ni * 8 + 2 * t;
+            double* dst = Dt + (long long)(wm * 32 + mi * 8 + g) * ldd + wn * 32 + ni * 8 + 2 * t;
             *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
 }
 
 // A(i,j)[half h] -= L(i,k)[half h] L(j,k)^T.  Diagonal tiles: only the 32x32 blocks on or below the diagonal.
-__device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int h, int j, int k, double* ring, int ltid, int grp) {
+//   mform: A(i,j)[half h] -= A'(i,k)[half h] M^T with M = L(j,k) W_k (the same product without L(i,k))
+__device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int h, int j, int k, double* ring, int ltid, int grp,
+                                         bool mform = false) {
     const int lw = ltid >> 5, lane = ltid & 31, g = lane >> 2, t = lane & 3;
     int wm, wn;
     warp_block(lw, wm, wn);
     const bool active = (i != j) || (wn <= 2 * h + wm);
-    const double* Ai = a.A + ((long long)i * CT + h * HR) * a.ld + (long long)k * CT;
-    const double* Aj = a.A + (long long)j * CT * a.ld + (long long)k * CT;
+    long long ldi, ldj;
+    const double* Ai;
+    const double* Aj;
+    if (mform) {
+        Ai = a.A + ((long long)i * CT + h * HR) * a.ld + (long long)k * CT; ldi = a.ld;
+        Aj = m_tile(a, j - k, k); ldj = CT;
+    } else {
+        Ai = l_tile(a, i, k, ldi) + (long long)h * HR * ldi;
+        Aj = l_tile(a, j, k, ldj);
+    }
     double* Ct = a.A + ((long long)i * CT + h * HR) * a.ld + (long long)j * CT;
     // accumulators start at -C: the loads overlap the ring's prologue, the result is -(acc)
     double acc[4][4][2];
@@ -233,7 +259,7 @@ __device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int h, int j
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             }
         }
-    half_mm(acc, Ai, a.ld, Aj, a.ld, wm, wn, active ? CT / CBK : 0, ring, ltid, grp);
+    half_mm(acc, Ai, ldi, Aj, ldj, wm, wn, active ? CT / CBK : 0, ring, ltid, grp);
     if (!active) return;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
@@ -341,12 +367,17 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
     int* err = a.flags;
     const int v = ((int)blockIdx.x - a.NG) * 2 + grp;          // worker group index
     const int t0 = a.tile_off[v], nt = a.tile_off[v + 1] - t0;
-    ChainTile my = {0, 0, 0, 0, 0, 0};
-    int next = 0;
+    ChainTile my = {0, 0, 0, 0, 0, 0, 0, 0};
+    int next = 0;                  // L-form updates applied (steps 0..next-1)
+    bool m1_done = true, m2_done = true;   // the M-form updates of steps j-1 (has_m bit 0) and j-2 (bit 1) applied, or none
     bool live = false;
     if (ltid < 32 && ltid < nt) {
         my = a.tiles[t0 + ltid];
-        live = (my.nupd > 0) || my.has_trsm;
+        m1_done = !(my.has_m & 1);
+        m2_done = !(my.has_m & 2);
+        live = (my.nupd > 0) || my.has_m || my.has_trsm;
+        // nothing to receive: complete from the start (the M-form readers of this tile poll it)
+        if (my.nupd == 0 && !my.has_m) st_release(f_cnt(a, my.i, my.h, my.j), C_COMPLETE);
     }
     long long w_wait = 0, w_trsm = 0, w_upd = 0, w_n = 0;
     for (;;) {
@@ -355,21 +386,33 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
             const int lane = ltid;
             const long long tp0 = clock64();
             unsigned it = 0;
-            int act = -1;
+            int act = -1, kind = 0;
             for (;;) {
-                bool ok = false;
+                // this tile's runnable task: 1 = M-form update of step j-2, 2 = of step j-1 (A'(i,kappa) complete and
+                // M_{j,kappa} published), 3 = TRSM (nothing else left, DIAG[j]), 4 = L-form update of step `next`
+                int cand = 0;
                 if (live) {
-                    if (next < (int)my.nupd) {
-                        ok = ld_acquire(f_lrh(a, my.i, my.h, next)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next)) >= 1 &&
-                             ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next)) >= 1);
-                    } else {
-                        ok = ld_acquire(f_diag(a, my.j)) >= 1;
-                    }
+                    const bool l_left = next < (int)my.nupd;
+                    // (a tile's updates are applied in step order -- L form 0..nupd-1, then j-2, then j-1 -- whatever the
+                    //  timing: the factor is bit-reproducible from run to run)
+                    if (!l_left && !m2_done) {
+                        if (ld_acquire(f_cnt(a, my.i, my.h, my.j - 2)) >= C_COMPLETE && ld_acquire(f_mp(a, 2, my.j - 2)) >= NH2) cand = 1;
+                    } else if (!l_left && !m1_done) {
+                        if (ld_acquire(f_cnt(a, my.i, my.h, my.j - 1)) >= C_COMPLETE && ld_acquire(f_mp(a, 1, my.j - 1)) >= NH2) cand = 2;
+                    } else if (!l_left) {
+                        if (ld_acquire(f_diag(a, my.j)) >= 1) cand = 3;
+                    } else if (ld_acquire(f_lrh(a, my.i, my.h, next)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next)) >= 1 &&
+                               ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next)) >= 1))
+                        cand = 4;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                // earliest deadline first over ALL runnable tasks: an update inherits its tile's deadline, a TRSM is
+                // consumed one step after its tile (by the step-j updates of row i); ties: M form / TRSM, then lane
+                unsigned key = 0xffffffffu;
+                if (cand) key = ((unsigned)(my.dl + (cand == 3 ? 1 : 0)) << 10) | (cand == 4 ? 256u : 0u) | ((unsigned)cand << 5) | (unsigned)lane;
+                const unsigned best = __reduce_min_sync(0xffffffffu, key);
                 const unsigned lv = __ballot_sync(0xffffffffu, live);
                 if (lv == 0u) { act = -2; break; }
-                if (m) { act = __ffs(m) - 1; break; }
+                if (best != 0xffffffffu) { act = (int)(best & 31u); kind = (int)((best >> 5) & 7u); break; }
                 if ((++it & 63u) == 0) {
                     int stop = 0;
                     if (lane == 0) {
@@ -380,30 +423,44 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                 }
             }
             if (act >= 0 && lane == act) {
-                const bool is_upd = next < (int)my.nupd;
-                s_task[grp * 4 + 0] = is_upd ? TASK_UPD : TASK_TRSM;
-                s_task[grp * 4 + 1] = ((int)my.i << 16) | (int)my.j;
-                s_task[grp * 4 + 2] = (int)my.h;
-                s_task[grp * 4 + 3] = is_upd ? next : (int)my.j;
-                next++;
-                live = is_upd ? (next < (int)my.nupd || my.has_trsm) : false;
+                int type, k;
+                if (kind == 1) { type = TASK_MUPD; k = my.j - 2; m2_done = true; }
+                else if (kind == 2) { type = TASK_MUPD; k = my.j - 1; m1_done = true; }
+                else if (kind == 3) { type = TASK_TRSM; k = my.j; live = false; }
+                else { type = TASK_UPD; k = next; next++; }
+                const bool complete = m1_done && m2_done && next >= (int)my.nupd;
+                if (type != TASK_TRSM && complete && !my.has_trsm) live = false;
+                s_task[grp * 6 + 0] = type;
+                s_task[grp * 6 + 1] = ((int)my.i << 16) | (int)my.j;
+                s_task[grp * 6 + 2] = (int)my.h;
+                s_task[grp * 6 + 3] = k;
+                s_task[grp * 6 + 4] = complete ? C_COMPLETE : next;
             }
             if (lane == 0) s_act[grp] = act;
         }
         group_bar(grp);
         const int act = s_act[grp];
-        if (act < 0) break;
-        const int type = s_task[grp * 4 + 0], ij = s_task[grp * 4 + 1], h = s_task[grp * 4 + 2], k = s_task[grp * 4 + 3];
+        if (act < 0) {
+            if (act == -1) return;          // aborted
+            break;
+        }
+        const int type = s_task[grp * 6 + 0], ij = s_task[grp * 6 + 1], h = s_task[grp * 6 + 2], k = s_task[grp * 6 + 3];
+        const int cnt = s_task[grp * 6 + 4];
         const int i = ij >> 16, j = ij & 0xffff;
         const long long tw1 = clock64();
         w_wait += tw1 - tw0;
+        long long* tc = a.tclk + ((long long)(2 * i + h) * a.T + j) * 4;
         if (type == TASK_TRSM) {
+            if (ltid == 0) tc[2] = gtimer_ns();
             task_trsm(a, i, h, k, ring, ltid, grp);
             publish_group(f_lrh(a, i, h, k), 1, ltid, grp);
+            if (ltid == 0) tc[3] = gtimer_ns();
             w_trsm += clock64() - tw1;
         } else {
-            task_upd(a, i, h, j, k, ring, ltid, grp);
-            publish_group(f_cnt(a, i, h, j), k + 1, ltid, grp);
+            if (ltid == 0 && cnt == C_COMPLETE) tc[0] = gtimer_ns();
+            task_upd(a, i, h, j, k, ring, ltid, grp, type == TASK_MUPD);
+            publish_group(f_cnt(a, i, h, j), cnt, ltid, grp);
+            if (ltid == 0 && cnt == C_COMPLETE) tc[1] = gtimer_ns();
             w_upd += clock64() - tw1;
         }
         w_n++;
@@ -411,6 +468,27 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
     if (ltid == 0) {
         a.wclk[v * 4 + 0] = w_wait; a.wclk[v * 4 + 1] = w_trsm;
         a.wclk[v * 4 + 2] = w_upd; a.wclk[v * 4 + 3] = w_n;
+    }
+    if (!a.mform) return;
+    // M-form mode: L(i,j) of this group's TRSMs sits in W's tile (i,j); move it home once the readers of A'(i,j) -- the
+    // M-form updates of tiles (i, j+1) and (i, j+2) -- are done.
+    for (int tix = 0; tix < nt; tix++) {
+        const ChainTile tl = a.tiles[t0 + tix];
+        if (!tl.has_trsm) continue;
+        if (ltid == 0) {
+            const bool ok = spin_ge(f_cnt(a, tl.i, tl.h, tl.j + 1), C_COMPLETE, err) && spin_ge(f_cnt(a, tl.i, tl.h, tl.j + 2), C_COMPLETE, err);
+            s_act[grp] = ok ? 1 : 0;
+        }
+        group_bar(grp);
+        if (!s_act[grp]) return;
+        const double* src = a.W + ((long long)tl.i * CT + tl.h * HR) * a.ldw + (long long)tl.j * CT;
+        double* dst = a.A + ((long long)tl.i * CT + tl.h * HR) * a.ld + (long long)tl.j * CT;
+        for (int e = ltid; e < HR * (CT / 2); e += 256) {
+            const int r = e >> 6, c2 = (e & 63) * 2;
+            *reinterpret_cast<double2*>(dst + (long long)r * a.ld + c2) =
+                __ldcg(reinterpret_cast<const double2*>(src + (long long)r * a.ldw + c2));
+        }
+        group_bar(grp);
     }
 }
 
@@ -539,6 +617,46 @@ __device__ __forceinline__ void strip_upd(const ChainArgs& a, int r, int j, int 
     }
 }
 
+// rows [r0, r0 + CR) of  M_{.,c} = L W_c  (L strip in shared memory, As; W_c is loaded into Bs unless it is there) ->
+// tile `slot` of step c in a.M, then this CTA's arrival on MP[slot][c]
+template <int CR>
+__device__ __forceinline__ void strip_m(const ChainArgs& a, int c, int r0, double* Bs, const double* As, int tid, int slot,
+                                        bool load_w) {
+    const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    if (load_w) {
+        const double* Wk = a.W + (long long)c * CT * a.ldw + (long long)c * CT;
+        for (int e = tid; e < CT * (CT / 2); e += CTHREADS) {
+            const int q = e >> 6, p2 = (e & 63) * 2;
+            if (p2 < ((q >> 5) + 1) * 32) cp_async16(Bs + q * CSLD + p2, Wk + (long long)q * a.ldw + p2);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    // warp w: columns [8w, 8w + 8); W_c is lower triangular: rows p >= 8w only
+    double acc[CR / 8][2];
+#pragma unroll
+    for (int mi = 0; mi < CR / 8; mi++) acc[mi][0] = acc[mi][1] = 0.0;
+    const double* ap = As + g * CSLD + t;
+    const double* bp = Bs + t * CSLD + wid * 8 + g;
+#pragma unroll 4
+    for (int kk = 2 * wid; kk < CT / 4; kk++) {
+        const double b = bp[kk * 4 * CSLD];
+#pragma unroll
+        for (int mi = 0; mi < CR / 8; mi++) dmma884(acc[mi][0], acc[mi][1], ap[mi * 8 * CSLD + kk * 4], b);
+    }
+    double* Mt = m_tile(a, slot, c) + (long long)r0 * CT;
+#pragma unroll
+    for (int mi = 0; mi < CR / 8; mi++)
+        *reinterpret_cast<double2*>(Mt + (mi * 8 + g) * CT + wid * 8 + 2 * t) = make_double2(acc[mi][0], acc[mi][1]);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(f_mp(a, slot, c), 1);
+        if (blockIdx.x == 1) a.tclk[(long long)2 * a.T * a.T * 4 + c * 4 + slot] = gtimer_ns();
+    }
+}
+
 __device__ __forceinline__ void publish(int* flag, int value, int tid) {
     __syncthreads();
     if (tid == 0) {
@@ -631,7 +749,6 @@ __device__ __forceinline__ void chain_group(const ChainArgs& a, double* csm, vol
 // needed by the WORKERS' TRSM tasks (one step of slack): the inverter CTA completes it from global memory and
 // publishes DIAG[k]; CTA 0 goes straight to the next diagonal block.
 // ===========================================================================
-constexpr int NH2 = 8;                  // helpers
 constexpr int CR2 = CT / NH2;           // 16 rows each
 constexpr int XLD = SB + 4;             // stride of 32-column operands (conflict-free fragment loads)
 
@@ -665,12 +782,20 @@ __device__ __forceinline__ void helper_v2(const ChainArgs& a, double* csm, volat
             if (tid == 0) {
                 const bool ok0 = spin_ge(f_diag(a, c), 1, err);
                 if (h == 0) a.wclk[g_hclk_off + 8 * 64 + k * 4 + 0] = gtimer_ns();
-                s_act[0] = (ok0 && spin_ge(f_cnt(a, k, half, c), c, err)) ? 1 : 0;
+                s_act[3] = ok0 ? 1 : 0;
             }
+            __syncthreads();
+            if (!s_act[3]) return;
+            // M-form: M_{c+1,c} = L(c+1,c) W_c first -- every row's update of its tile (i, c+1) waits for it.  This CTA's
+            // strip of L(c+1,c) = L(d,c) is still in As from the previous iteration's pipelined columns.
+            if (a.mform) strip_m<CR2>(a, c, r0, Bs, As, tid, 1, true);
+            if (tid == 0) s_act[0] = spin_ge(f_cnt(a, k, half, c), c, err) ? 1 : 0;
             __syncthreads();
             if (!s_act[0]) return;
             HSTAMP(1);
             strip_trsm<CR2>(a, k, r0, Bs, As1, tid, c);
+            // M_{c+2,c} = L(k,c) W_c for the last worker-side update of tile (c+3, c+2); W_c is still in Bs
+            if (a.mform >= 3) { __syncthreads(); strip_m<CR2>(a, c, r0, Bs, As1, tid, 2, false); }
             HSTAMP(2);
             arrive(f_ux(a, k), NH2, f_lrh(a, k, 0, c), f_lrh(a, k, 1, c), tid);
             if (tid == 0) s_act[1] = (spin_ge(f_cnt(a, k, half, d), d - 1, err) && spin_ge(f_xp(a, d, 3), NH2, err)) ? 1 : 0;
@@ -772,6 +897,38 @@ __device__ __forceinline__ void helper_v2(const ChainArgs& a, double* csm, volat
                 }
             }
             __syncthreads();            // Lk / Xa are reloaded by the next block column
+            if (bb == 0 && a.mform >= 3 && k >= 3) {
+                // M-form mode: step k-3 of the diagonal tile is this group's too (a TRSM -> update chain of the workers
+                // inside one step otherwise): acc += L(k,k-3)[strip] L(k,k-3)^T, in the idle time before block column 1.
+                // L(k,k-3) is a worker TRSM: it sits in W's tile.
+                const int c3 = k - 3;
+                if (tid == 0) s_act[1] = (spin_ge(f_lrh(a, k, 0, c3), 1, err) && spin_ge(f_lrh(a, k, 1, c3), 1, err)) ? 1 : 0;
+                __syncthreads();
+                if (!s_act[1]) return;
+                const double* Ls = a.W + (long long)k * CT * a.ldw + (long long)c3 * CT;
+                for (int e = tid; e < CR2 * (CT / 2); e += CTHREADS) {
+                    const int r = e >> 6, p2 = (e & 63) * 2;
+                    cp_async16(As1 + r * CSLD + p2, Ls + (long long)(r0 + r) * a.ldw + p2);
+                }
+                for (int e = tid; e < ncol * (CT / 2); e += CTHREADS) {
+                    const int r = e >> 6, p2 = (e & 63) * 2;
+                    cp_async16(Bs + r * CSLD + p2, Ls + (long long)r * a.ldw + p2);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                if (wid * 8 < ncol) {
+                    const double* ap = As1 + g * CSLD + t;
+                    const double* bp_ = Bs + (wid * 8 + g) * CSLD + t;
+#pragma unroll 4
+                    for (int kk = 0; kk < CT / 4; kk++) {
+                        const double b = bp_[kk * 4];
+#pragma unroll
+                        for (int m = 0; m < CR2 / 8; m++) dmma884(acc[m][0], acc[m][1], ap[m * 8 * CSLD + kk * 4], b);
+                    }
+                }
+                __syncthreads();
+            }
         }
         // C strip -= sum_bb X[:, bb] X_all[:, bb]^T   (the tile's earlier steps: workers, then the urgent phase above)
         if (wid * 8 < ncol) {
@@ -873,6 +1030,7 @@ __device__ __forceinline__ void inverter_v2(const ChainArgs& a, double* csm, vol
         if (tid == 0) {
             __threadfence();
             st_release(f_diag(a, k), 1);
+            a.tclk[(long long)2 * a.T * a.T * 4 + k * 4 + 0] = gtimer_ns();
             a.wclk[g_hclk_off + 8 * 64 + k * 4 + 2] = gtimer_ns();
         }
     }
@@ -890,6 +1048,7 @@ __device__ __forceinline__ void chain0_v2(const ChainArgs& a, double* csm, volat
             if (!s_act[0]) { if (tid == 0) *a.info = -999; return; }
         }
         CHAIN_STAMP(k, 5);
+        if (tid == 0) a.tclk[(long long)2 * a.T * a.T * 4 + k * 4 + 3] = gtimer_ns();
         const long long o = (long long)k * CT;
         const long long valid = (long long)a.n_valid - o;
         const int nsub = valid >= CT ? 4 : (valid <= 0 ? 0 : (int)((valid + SB - 1) / SB));
@@ -907,6 +1066,8 @@ __device__ __forceinline__ void chain0_v2(const ChainArgs& a, double* csm, volat
                 __threadfence();
                 for (int bb = 0; bb < 4; bb++) st_release(f_lpub(a, k, bb), 1);
                 st_release(f_diag(a, k), 1);
+                a.tclk[(long long)2 * a.T * a.T * 4 + k * 4 + 0] = gtimer_ns();
+            a.tclk[(long long)2 * a.T * a.T * 4 + k * 4 + 0] = gtimer_ns();
             }
         }
         CHAIN_STAMP(k, 6);
@@ -918,7 +1079,7 @@ __device__ __forceinline__ void chain0_v2(const ChainArgs& a, double* csm, volat
 __global__ void __launch_bounds__(CTHREADS, 1) potrf_dataflow_kernel(const ChainArgs a) {
     extern __shared__ __align__(16) double csm[];
     __shared__ int s_act[4];
-    __shared__ int s_task[8];
+    __shared__ int s_task[12];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < a.NG) {
         if (a.pipelined) {
@@ -947,13 +1108,14 @@ std::map<cudaStream_t, std::pair<int*, size_t>> g_flag_pool;
 std::map<cudaStream_t, int> g_last_T;
 std::mutex g_plan_mu;
 
-int build_plan(int T, int G, int NG, ChainPlan* out) {
+int build_plan(int T, int G, int NG, int mform, ChainPlan* out) {
     const bool pipelined = (NG == NH2 + 2);
     const bool express = gpb_get_option("chain_express") == 1;
+    NG += 1000 * mform;              // (plan cache key only)
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto it = g_plans.find({{T, G}, NG + (express ? 100 : 0)});
     if (it != g_plans.end()) { *out = it->second; return GPB_OK; }
-    const int nv = 2 * (G - NG);            // worker groups
+    const int nv = 2 * (G - NG % 1000);     // worker groups
     // pipelined group: worker groups 0..3 are EXPRESS groups.  Per step s they run exactly the tasks the chain group
     // waits for one step later -- TRSM(s+3, s) and the step-s updates of tiles (s+3, s+1), (s+3, s+2), (s+3, s+3) -- and
     // nothing else, so those tasks never queue behind a regular group's 20-40 k-cycle backlog.
@@ -1032,25 +1194,40 @@ int build_plan(int T, int G, int NG, ChainPlan* out) {
             for (int i = j; i < T; i++)
                 for (int h = 0; h < 2; h++) {
                     int dl = j;
-                    if (pipelined) dl = j - (i == j ? 2 : (i == j + 1 ? 1 : 0));
+                    if (pipelined) dl = j - (i == j ? (mform >= 3 ? 3 : 2) : (i == j + 1 ? 1 : 0));
                     else dl = j - (i == j ? 1 : 0);
                     order.push_back({{dl, j}, {i, h}});
                 }
         std::sort(order.begin(), order.end());
         for (auto& o : order) {
             const int j = o.first.second, i = o.second.first, h = o.second.second;
-            int nupd = j, has_trsm;
+            int nupd = j, has_trsm, has_m = 0;
             if (pipelined) {
                 has_trsm = i >= j + 3;
                 if (i == j) nupd = j - 2;           // steps j-2 (urgent phase) and j-1 (pipelined columns) are the helpers'
                 if (i == j + 1) nupd = j - 1;       // step j-1 is the helpers' urgent phase
+                // M form: the tile's last worker-side step (kappa = nupd - 1) reads A'(i,kappa) instead of L(i,kappa)
+                // M form (level 1): step j-1 of the tiles below the first sub-diagonal reads A'(i,j-1) and M_{j,j-1}
+                // instead of L(i,j-1).  Level 3: also step j-2 of the first sub-diagonal tiles (M_{j,j-2}), and step j-3
+                // of the diagonal tiles moves to the helpers (folded into their pipelined columns).  Level 4: step j-2
+                // of every tile below the diagonal in M form.
+                if (mform >= 3 && i == j) nupd = j - 3;
+                if (mform >= 4 && i >= j + 1) {
+                    nupd = j - 2;
+                    if (j >= 2) has_m |= 2;
+                    if (i >= j + 2 && j >= 1) has_m |= 1;
+                } else if (mform >= 1) {
+                    if (i >= j + 2 && j >= 1) { nupd = j - 1; has_m |= 1; }
+                    if (mform >= 3 && i == j + 1 && j >= 2) { nupd = j - 2; has_m |= 2; }
+                }
             } else {
                 has_trsm = i >= j + 2;
                 if (i == j) nupd = j - 1;
             }
             if (nupd < 0) nupd = 0;
             auto& l = tl[owner(i, h, j)];
-            l.push_back({(short)i, (short)j, (unsigned char)h, (unsigned char)nupd, (unsigned char)has_trsm, 0});
+            l.push_back({(short)i, (short)j, (unsigned char)h, (unsigned char)nupd, (unsigned char)has_trsm, (unsigned char)has_m,
+                         (short)(o.first.first < 0 ? 0 : o.first.first), 0});
             if (l.size() > most) most = l.size();
         }
         if (most <= 32) {
@@ -1084,7 +1261,10 @@ int chain_init() {
     return GPB_OK;
 }
 
-size_t chain_pool_words(int T) { return (chain_flag_words(T) + 1) / 2 * 2 + (size_t)T * 16 + (size_t)(g_hclk_off + 12 * 64 + 8) * 2; }
+// flags and clocks (zeroed before every launch), then the M tiles
+size_t chain_zero_words(int T) { return (chain_flag_words(T) + 3) / 4 * 4 + (size_t)T * 16 + (size_t)(g_hclk_off + 12 * 64 + 8) * 2; }
+size_t chain_trace_lls(int T) { return (size_t)2 * T * T * 4 + (size_t)T * 4; }
+size_t chain_pool_words(int T) { return chain_zero_words(T) + (size_t)3 * T * CT * CT * 2 + chain_trace_lls(T) * 2; }
 
 }  // namespace
 
@@ -1112,7 +1292,12 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     int G = (int)(((nhalf + 1) / 2 + NG < (long long)num_sms) ? (nhalf + 1) / 2 + NG : num_sms);
     if (G < NG + 1) G = NG + 1;
     ChainPlan plan;
-    stt = build_plan(T, G, NG, &plan);
+    const bool lists = gpb_get_option("chain_sched") == 1;       // 1 = in-order task lists, 0 = most urgent runnable tile first
+    // 0 = M form whenever the tile scheduler and the pipelined group run, 2 = off
+    int mform = gpb_get_option("chain_mform");      // 0 -> level 1; 2 = off; 1, 3, 4 = levels (build_plan)
+    if (mform == 0) mform = 1;
+    if (mform == 2 || !pipelined || lists || gpb_get_option("chain_express") == 1) mform = 0;
+    stt = build_plan(T, G, NG, mform, &plan);
     if (stt) return stt;
     // flag words: one grow-only set per stream (two factorisations on one stream are serialised anyway)
     // (+ the chain's phase clocks, 8 per step, and the workers' accounting behind the flags)
@@ -1130,15 +1315,17 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
         flags = e.first;
         g_last_T[st] = T;
     }
-    GPB_CUDA(cudaMemsetAsync(flags, 0, nfl * sizeof(int), st));
+    GPB_CUDA(cudaMemsetAsync(flags, 0, chain_zero_words(T) * sizeof(int), st));
     ChainArgs a;
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = V; a.ldv = ldv; a.info = info;
     a.T = T; a.n_valid = (int)n_valid; a.flags = flags;
     a.bulk = plan.bulk; a.bulk_off = plan.bulk_off; a.trsm = plan.trsm; a.trsm_off = plan.trsm_off;
-    const bool lists = gpb_get_option("chain_sched") == 1;       // 1 = in-order task lists, 0 = most urgent runnable tile first
     a.tiles = lists ? nullptr : plan.tiles; a.tile_off = lists ? nullptr : plan.tile_off;
-    a.clk = reinterpret_cast<long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2);
+    a.clk = reinterpret_cast<long long*>(flags + (chain_flag_words(T) + 3) / 4 * 4);
     a.wclk = a.clk + (size_t)T * 8;
+    a.M = reinterpret_cast<double*>(flags + chain_zero_words(T));
+    a.tclk = reinterpret_cast<long long*>(a.M + (size_t)3 * T * CT * CT);
+    a.mform = a.tiles ? mform : 0;
     a.NG = NG;
     a.pipelined = pipelined;
     a.diag512 = gpb_get_option("chain_diag");           // 0/1 default body, 2 the 256-thread body, 3.. experiments
@@ -1173,8 +1360,22 @@ extern "C" int gpb_debug_chain_clocks(void* stream, long long* out, int max_step
     int stt = chain_debug_pool(stream, &flags, &T);
     if (stt) return stt;
     const int n = T < max_steps ? T : max_steps;
-    const long long* clk = reinterpret_cast<const long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2);
+    const long long* clk = reinterpret_cast<const long long*>(flags + (chain_flag_words(T) + 3) / 4 * 4);
     GPB_CUDA(cudaMemcpy(out, clk, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return T;
+}
+
+// %globaltimer trace of the same launch: [2T][T][4] per half tile (last update start | complete | TRSM start | TRSM done), then
+// [T][4] per step (DIAG published | helper 0's M1 | M2 arrival | the chain CTA starts the diagonal block).  Returns T.
+extern "C" int gpb_debug_chain_tiles(void* stream, long long* out, long long max_lls) {
+    int* flags = nullptr;
+    int T = 0;
+    int stt = chain_debug_pool(stream, &flags, &T);
+    if (stt) return stt;
+    size_t n = chain_trace_lls(T);
+    if ((long long)n > max_lls) n = (size_t)max_lls;
+    const long long* src = reinterpret_cast<const long long*>(reinterpret_cast<const double*>(flags + chain_zero_words(T)) + (size_t)3 * T * CT * CT);
+    GPB_CUDA(cudaMemcpy(out, src, n * sizeof(long long), cudaMemcpyDeviceToHost));
     return T;
 }
 
@@ -1185,7 +1386,7 @@ extern "C" int gpb_debug_chain_workers(void* stream, long long* out, int max_gro
     int stt = chain_debug_pool(stream, &flags, &T);
     if (stt) return stt;
     if (max_groups > (g_hclk_off + 12 * 64) / 4) max_groups = (g_hclk_off + 12 * 64) / 4;
-    const long long* clk = reinterpret_cast<const long long*>(flags + (chain_flag_words(T) + 1) / 2 * 2) + (size_t)T * 8;
+    const long long* clk = reinterpret_cast<const long long*>(flags + (chain_flag_words(T) + 3) / 4 * 4) + (size_t)T * 8;
     GPB_CUDA(cudaMemcpy(out, clk, (size_t)max_groups * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
     return T;
 }
@@ -1221,7 +1422,7 @@ extern "C" int gpb_debug_tile_bench(double* A, long long ld, double* W, long lon
         attr_set = true;
     }
     ChainArgs a;
-    a.tiles = nullptr; a.tile_off = nullptr;
+    a.tiles = nullptr; a.tile_off = nullptr; a.mform = 0; a.M = nullptr; a.tclk = nullptr;
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = nullptr; a.ldv = 0; a.info = nullptr; a.T = 3; a.n_valid = 0;
     a.NG = 8; a.pipelined = 0; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
     a.clk = nullptr; a.wclk = nullptr;

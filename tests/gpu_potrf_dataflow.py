@@ -8,7 +8,7 @@ import torch
 from gaussian_processes_b200 import _lib, engine, device as D
 from conftest import synth_xy
 
-sizes = [int(a) for a in sys.argv[1:] if not a.startswith(("d", "g", "s", "e"))] or [256, 384, 1024, 2048, 4096, 8192]
+sizes = [int(a) for a in sys.argv[1:] if not a.startswith(("d", "g", "s", "e", "m"))] or [256, 384, 1024, 2048, 4096, 8192]
 for a in sys.argv[1:]:
     if a.startswith("d"):
         _lib.set_option("chain_diag", int(a[1:]))
@@ -16,6 +16,8 @@ for a in sys.argv[1:]:
         _lib.set_option("chain_group", int(a[1:]))
     if a.startswith("s"):
         _lib.set_option("chain_sched", int(a[1:]))
+    if a.startswith("m"):
+        _lib.set_option("chain_mform", int(a[1:]))
     if a.startswith("e"):
         _lib.set_option("chain_express", int(a[1:]))
 for nn in sizes:
@@ -78,6 +80,11 @@ for ph in range(10):
     print("  %s warp arrivals (cycles since block start):" % names[ph], arr[ph].tolist())
 hc = w[(1280 + 256) // 4:(1280 + 256 + 8 * T) // 4].reshape(-1)[:8 * T].reshape(T, 8)
 kk = min(T - 2, max(2, T // 2))
+print("helper 0 waits per step (cycles): urgent inputs", (hc[2:, 1] - hc[2:, 0]).tolist())
+print("helper 0 waits per step (cycles): upd inputs   ", (hc[2:, 3] - hc[2:, 2]).tolist())
+print("helper 0 waits per step (cycles): syrk inputs  ", (hc[2:, 5] - hc[2:, 4]).tolist())
+print("helper 0 iteration length per step (cycles)    ", (hc[2:, 7] - hc[2:, 0]).tolist())
+print("chain CTA waits per step (cycles)              ", (c[1:, 5] - c[1:, 0]).tolist())
 print("helper 0 at step %d (cycles rel. to the chain CTA's step start): start %d | urgent: inputs ready %d, trsm done %d, upd inputs ready %d, upd done %d, syrk inputs ready %d, syrk done %d | end %d || chain CTA: tile ready %d, diag done %d" % (
     (kk,) + tuple((hc[kk, :8] - c[kk - 1, 0]).tolist()) + (c[kk - 1, 5] - c[kk - 1, 0], c[kk - 1, 6] - c[kk - 1, 0])))
 h2 = w[(1280 + 256 + 8 * 64) // 4:(1280 + 256 + 12 * 64) // 4].reshape(-1)[:4 * T].reshape(T, 4)
