@@ -83,6 +83,7 @@ struct ChainArgs {
     int NG;                     // CTAs of the chain group (CTA 0 = the chain, 1..NG-1 its helpers)
     int diag512;                // 1: full diagonal blocks by the 512-thread body (diag_block512.cuh)
     int pipelined;              // 1: chain group v2 (c0 publishes every 32-column block; helpers one block behind; inverter CTA)
+    int fuse;                   // most steps of one half tile's backlog applied in one task (K = 128 * steps)
     int mform;                  // 1: last worker update of a tile in M form, worker TRSMs out of place (see worker_group_edf)
     long long* tclk;            // trace (%globaltimer): [2T][T][4] per half tile: last update start | complete | TRSM start | done; then [T][4]
     double* M;                  // [3][T] tiles [128][128]: M_{k+c,k} = L(k+c,k) W_k  (c = 1..3)
@@ -154,8 +155,8 @@ __device__ __forceinline__ void ring_load(double* sdst, const double* g, long lo
 // acc += sum_k Ag[r, k] * Bg[c, k], K = 128, for this warp's 32 x 32 block (wm, wn) of a 64 x 128 half tile;
 // the warp multiplies only k-chunks [0, kt_hi), but walks all chunks (loads and barriers are group-wide)
 __device__ __forceinline__ void half_mm(double (&acc)[4][4][2], const double* Ag, long long lda, const double* Bg,
-                                        long long ldb, int wm, int wn, int kt_hi, double* ring, int ltid, int grp) {
-    constexpr int NK = CT / CBK;
+                                        long long ldb, int wm, int wn, int kt_hi, double* ring, int ltid, int grp,
+                                        int NK = CT / CBK) {
     const int lane = ltid & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int s = 0; s < GSTAGES - 1; s++) {
@@ -228,8 +229,9 @@ __device__ __forceinline__ void task_trsm(const ChainArgs& a, int i, int h, int 
 
 // A(i,j)[half h] -= L(i,k)[half h] L(j,k)^T.  Diagonal tiles: only the 32x32 blocks on or below the diagonal.
 //   mform: A(i,j)[half h] -= A'(i,k)[half h] M^T with M = L(j,k) W_k (the same product without L(i,k))
+//   nk > 1: steps k..k+nk-1 in one pass (K = 128 nk; the operands of consecutive steps are adjacent columns)
 __device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int h, int j, int k, double* ring, int ltid, int grp,
-                                         bool mform = false) {
+                                         bool mform = false, int nk = 1) {
     const int lw = ltid >> 5, lane = ltid & 31, g = lane >> 2, t = lane & 3;
     int wm, wn;
     warp_block(lw, wm, wn);
@@ -259,7 +261,7 @@ __device__ __forceinline__ void task_upd(const ChainArgs& a, int i, int h, int j
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
             }
         }
-    half_mm(acc, Ai, ldi, Aj, ldj, wm, wn, active ? CT / CBK : 0, ring, ltid, grp);
+    half_mm(acc, Ai, ldi, Aj, ldj, wm, wn, active ? nk * (CT / CBK) : 0, ring, ltid, grp, nk * (CT / CBK));
     if (!active) return;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
@@ -386,11 +388,12 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
             const int lane = ltid;
             const long long tp0 = clock64();
             unsigned it = 0;
-            int act = -1, kind = 0;
+            int act = -1, kind = 0, nfuse = 1;
             for (;;) {
                 // this tile's runnable task: 1 = M-form update of step j-2, 2 = of step j-1 (A'(i,kappa) complete and
                 // M_{j,kappa} published), 3 = TRSM (nothing else left, DIAG[j]), 4 = L-form update of step `next`
                 int cand = 0;
+                nfuse = 1;
                 if (live) {
                     const bool l_left = next < (int)my.nupd;
                     // (a tile's updates are applied in step order -- L form 0..nupd-1, then j-2, then j-1 -- whatever the
@@ -402,8 +405,15 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                     } else if (!l_left) {
                         if (ld_acquire(f_diag(a, my.j)) >= 1) cand = 3;
                     } else if (ld_acquire(f_lrh(a, my.i, my.h, next)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next)) >= 1 &&
-                               ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next)) >= 1))
+                               ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next)) >= 1)) {
                         cand = 4;
+                        // backlog: the following steps too, while their operands are final and live in the same
+                        // buffer as this step's (M-form mode: L(r,s) is in W for r >= s + 3, the chain's rows in A)
+                        while (nfuse < a.fuse && next + nfuse < (int)my.nupd && (!a.mform || next + nfuse <= my.j - 3) &&
+                               ld_acquire(f_lrh(a, my.i, my.h, next + nfuse)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next + nfuse)) >= 1 &&
+                               ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next + nfuse)) >= 1))
+                            nfuse++;
+                    }
                 }
                 // earliest deadline first over ALL runnable tasks: an update inherits its tile's deadline, a TRSM is
                 // consumed one step after its tile (by the step-j updates of row i); ties: M form / TRSM, then lane
@@ -427,7 +437,7 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                 if (kind == 1) { type = TASK_MUPD; k = my.j - 2; m2_done = true; }
                 else if (kind == 2) { type = TASK_MUPD; k = my.j - 1; m1_done = true; }
                 else if (kind == 3) { type = TASK_TRSM; k = my.j; live = false; }
-                else { type = TASK_UPD; k = next; next++; }
+                else { type = TASK_UPD; k = next; next += nfuse; }
                 const bool complete = m1_done && m2_done && next >= (int)my.nupd;
                 if (type != TASK_TRSM && complete && !my.has_trsm) live = false;
                 s_task[grp * 6 + 0] = type;
@@ -435,6 +445,7 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                 s_task[grp * 6 + 2] = (int)my.h;
                 s_task[grp * 6 + 3] = k;
                 s_task[grp * 6 + 4] = complete ? C_COMPLETE : next;
+                s_task[grp * 6 + 5] = (type == TASK_UPD) ? nfuse : 1;
             }
             if (lane == 0) s_act[grp] = act;
         }
@@ -458,7 +469,7 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
             w_trsm += clock64() - tw1;
         } else {
             if (ltid == 0 && cnt == C_COMPLETE) tc[0] = gtimer_ns();
-            task_upd(a, i, h, j, k, ring, ltid, grp, type == TASK_MUPD);
+            task_upd(a, i, h, j, k, ring, ltid, grp, type == TASK_MUPD, s_task[grp * 6 + 5]);
             publish_group(f_cnt(a, i, h, j), cnt, ltid, grp);
             if (ltid == 0 && cnt == C_COMPLETE) tc[1] = gtimer_ns();
             w_upd += clock64() - tw1;
@@ -1273,7 +1284,7 @@ size_t chain_pool_words(int T) { return chain_zero_words(T) + (size_t)3 * T * CT
 // lives in L2 and the K = 128 updates re-stream it from HBM every step; potrf.cu's look-ahead panels win.
 bool gpb_potrf_dataflow_ok(long long n, int batch) {
     const long long T = n / GPB_NB;
-    return batch == 1 && T >= 2 && T <= 48;
+    return batch == 1 && T >= 2 && T <= 64;
 }
 
 // zero_blocks and info initialisation are the caller's (gpb_launch_potrf) business
@@ -1326,6 +1337,8 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     a.M = reinterpret_cast<double*>(flags + chain_zero_words(T));
     a.tclk = reinterpret_cast<long long*>(a.M + (size_t)3 * T * CT * CT);
     a.mform = a.tiles ? mform : 0;
+    a.fuse = gpb_get_option("chain_fuse");            // 0 -> default
+    if (a.fuse <= 0) a.fuse = 4;             // measured 1 / 2 / 3 / 4 / 8 at N = 4096: 1.68 / 1.65 / 1.60 / 1.59 / 1.59 ms, N = 6144: 4.15 / 3.83 / 3.72 / 3.69 / 3.79
     a.NG = NG;
     a.pipelined = pipelined;
     a.diag512 = gpb_get_option("chain_diag");           // 0/1 default body, 2 the 256-thread body, 3.. experiments
@@ -1422,7 +1435,7 @@ extern "C" int gpb_debug_tile_bench(double* A, long long ld, double* W, long lon
         attr_set = true;
     }
     ChainArgs a;
-    a.tiles = nullptr; a.tile_off = nullptr; a.mform = 0; a.M = nullptr; a.tclk = nullptr;
+    a.tiles = nullptr; a.tile_off = nullptr; a.mform = 0; a.fuse = 1; a.M = nullptr; a.tclk = nullptr;
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = nullptr; a.ldv = 0; a.info = nullptr; a.T = 3; a.n_valid = 0;
     a.NG = 8; a.pipelined = 0; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
     a.clk = nullptr; a.wclk = nullptr;
