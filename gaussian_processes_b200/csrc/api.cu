@@ -84,6 +84,7 @@ static GpbOption g_options[] = {
     {"chain_express", "GPB_CHAIN_EXPRESS", 0, false},       // 1 = six express worker groups for the chain-adjacent tiles (measured: no gain)
     {"chain_mform", "GPB_CHAIN_MFORM", 0, false},           // M form of the workers' last update(s) of a tile: 0/1 = step j-1, 3, 4 = more (chain.cu build_plan), 2 = off
     {"chain_fuse", "GPB_CHAIN_FUSE", 0, false},             // most backlog steps of a half tile applied by one worker task (default 4)
+    {"chain_fuse_guard", "GPB_CHAIN_FUSE_GUARD", 0, false}, // no fused task while a more urgent tile of the group is due within this many steps (default 2, 100 = off)
     {"chain_sched", "GPB_CHAIN_SCHED", 0, false},           // workers: 0 = most urgent runnable half tile first, 1 = in-order task lists
     {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = the first chain group of that many CTAs
 };

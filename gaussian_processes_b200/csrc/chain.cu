@@ -83,6 +83,7 @@ struct ChainArgs {
     int NG;                     // CTAs of the chain group (CTA 0 = the chain, 1..NG-1 its helpers)
     int diag512;                // 1: full diagonal blocks by the 512-thread body (diag_block512.cuh)
     int pipelined;              // 1: chain group v2 (c0 publishes every 32-column block; helpers one block behind; inverter CTA)
+    int fuse_guard;             // ... unless a more urgent tile of the group is due within this many steps
     int fuse;                   // most steps of one half tile's backlog applied in one task (K = 128 * steps)
     int mform;                  // 1: last worker update of a tile in M form, worker TRSMs out of place (see worker_group_edf)
     long long* tclk;            // trace (%globaltimer): [2T][T][4] per half tile: last update start | complete | TRSM start | done; then [T][4]
@@ -394,6 +395,9 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                 // M_{j,kappa} published), 3 = TRSM (nothing else left, DIAG[j]), 4 = L-form update of step `next`
                 int cand = 0;
                 nfuse = 1;
+                // the group's most urgent live tile: a long fused task must not start when that tile's last updates
+                // are about to become runnable (tasks are not preempted)
+                const int dmin = (int)__reduce_min_sync(0xffffffffu, live ? (unsigned)my.dl : 0x7fffffffu);
                 if (live) {
                     const bool l_left = next < (int)my.nupd;
                     // (a tile's updates are applied in step order -- L form 0..nupd-1, then j-2, then j-1 -- whatever the
@@ -410,6 +414,7 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                         // backlog: the following steps too, while their operands are final and live in the same
                         // buffer as this step's (M-form mode: L(r,s) is in W for r >= s + 3, the chain's rows in A)
                         while (nfuse < a.fuse && next + nfuse < (int)my.nupd && (!a.mform || next + nfuse <= my.j - 3) &&
+                               (my.dl == dmin || next + nfuse + a.fuse_guard <= dmin) &&
                                ld_acquire(f_lrh(a, my.i, my.h, next + nfuse)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next + nfuse)) >= 1 &&
                                ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next + nfuse)) >= 1))
                             nfuse++;
@@ -1338,6 +1343,9 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     a.tclk = reinterpret_cast<long long*>(a.M + (size_t)3 * T * CT * CT);
     a.mform = a.tiles ? mform : 0;
     a.fuse = gpb_get_option("chain_fuse");            // 0 -> default
+    a.fuse_guard = gpb_get_option("chain_fuse_guard");
+    if (a.fuse_guard <= 0) a.fuse_guard = 2;
+    if (a.fuse_guard >= 100) a.fuse_guard = -1000;       // (off)
     if (a.fuse <= 0) a.fuse = 4;             // measured 1 / 2 / 3 / 4 / 8 at N = 4096: 1.68 / 1.65 / 1.60 / 1.59 / 1.59 ms, N = 6144: 4.15 / 3.83 / 3.72 / 3.69 / 3.79
     a.NG = NG;
     a.pipelined = pipelined;
@@ -1435,7 +1443,7 @@ extern "C" int gpb_debug_tile_bench(double* A, long long ld, double* W, long lon
         attr_set = true;
     }
     ChainArgs a;
-    a.tiles = nullptr; a.tile_off = nullptr; a.mform = 0; a.fuse = 1; a.M = nullptr; a.tclk = nullptr;
+    a.tiles = nullptr; a.tile_off = nullptr; a.mform = 0; a.fuse = 1; a.fuse_guard = 2; a.M = nullptr; a.tclk = nullptr;
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = nullptr; a.ldv = 0; a.info = nullptr; a.T = 3; a.n_valid = 0;
     a.NG = 8; a.pipelined = 0; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
     a.clk = nullptr; a.wclk = nullptr;

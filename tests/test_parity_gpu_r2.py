@@ -388,3 +388,81 @@ def test_gp_c_c_abi_direct_ctypes():
     K = np.ascontiguousarray(g["Kxx"])
     assert lib.gpb_gp_c_log_lh(y.ctypes.data, K.ctypes.data, a.ctypes.data, n, ctypes.byref(llh)) == 0
     assert_parity(llh.value, g["log_lh"])
+
+
+# ------------------------------------------------------------------ dataflow Cholesky (csrc/chain.cu)
+DATAFLOW_VARIANTS = [
+    {},                                            # default: pipelined chain group, tile scheduler, M form, fused backlog
+    {"chain_sched": 1},                            # in-order task lists
+    {"chain_mform": 2}, {"chain_mform": 3}, {"chain_mform": 4},
+    {"chain_fuse": 1}, {"chain_fuse": 8, "chain_fuse_guard": 100},
+    {"chain_group": 8}, {"chain_group": 4}, {"chain_sched": 1, "chain_express": 1},
+]
+
+
+def _factor_one(n, options, poke=None):
+    """gpb_potrf of one N x N Gaussian Kxx (+ s^2 I, identity-padded to a multiple of 128) -> (L, W diag blocks, info)."""
+    import torch
+    from gaussian_processes_b200 import _lib, engine, device as D
+    x, y = synth_xy(n, 0)
+    eng = engine.Engine(engine.GAUSSIAN, (1.0, 0.5), 1.0, x, y)
+    npad = (n + 127) // 128 * 128
+    for k, v in options.items():
+        _lib.set_option(k, v)
+    try:
+        W, V, info = D.zeros(npad, npad), D.zeros(npad, npad), D.izeros(1)
+        A = eng.build(eng.dx, n, eng.dx, n, npad, npad, 1, add_diag=True, pad_identity=True)[0]
+        K = A.clone()
+        if poke is not None:
+            A[poke, poke] = -1.0
+        _lib.call("gpb_potrf", D.ptr(A), npad, npad, 0, 1, D.ptr(W), npad, 0, D.ptr(V), npad, 0, D.ptr(info), D.stream_ptr())
+        torch.cuda.synchronize()
+        Wd = torch.stack([W[b:b + 128, b:b + 128] for b in range(0, npad, 128)])
+        return torch.tril(A), Wd, int(info.item()), K
+    finally:
+        for k in options:
+            _lib.set_option(k, 0)
+
+
+@pytest.mark.parametrize("n", [256, 600, 1152, 2048])
+def test_dataflow_potrf_variants_agree_with_launch_sequence(n):
+    """Every scheduling variant of the persistent dataflow factorisation gives the factor of the launch-sequence
+    schedule (potrf_dataflow = 2) to rounding, L L^T = K, and the same inverted diagonal blocks."""
+    import torch
+    L0, W0, i0, K = _factor_one(n, {"potrf_dataflow": 2})
+    assert i0 == 0
+    scale = float(L0.abs().max())
+    for opts in DATAFLOW_VARIANTS:
+        L1, W1, i1, _ = _factor_one(n, dict(opts))
+        assert i1 == 0, opts
+        assert not bool(torch.isnan(L1).any()), opts
+        assert float((L1 - L0).abs().max()) <= 1e-12 * scale, (opts, float((L1 - L0).abs().max()))
+        assert float((W1 - W0).abs().max()) <= 1e-11 * float(W0.abs().max()), opts
+        R = torch.tril(L1 @ L1.T - K)
+        assert float(R.abs().max()) <= 1e-13 * float(K.abs().max()) * n, opts
+    # run-to-run reproducible bit for bit (updates of a tile are applied in a fixed order)
+    La, _, _, _ = _factor_one(n, {})
+    Lb, _, _, _ = _factor_one(n, {})
+    assert torch.equal(La, Lb)
+
+
+@pytest.mark.parametrize("poke", [5, 700, 1023])
+def test_dataflow_potrf_reports_the_failing_column(poke):
+    """A matrix that stops being positive definite at column `poke`: info = poke + 1 (LAPACK convention) from every
+    variant, and the launch terminates (no worker waits for a tile that never completes)."""
+    _, _, i0, _ = _factor_one(1024, {"potrf_dataflow": 2}, poke=poke)
+    assert i0 == poke + 1
+    for opts in DATAFLOW_VARIANTS[:6]:
+        _, _, i1, _ = _factor_one(1024, dict(opts), poke=poke)
+        assert i1 == poke + 1, opts
+
+
+def test_gp_not_positive_definite_above_one_block():
+    """LinAlgError / -inf / NaN semantics of the reference (gp.py:294, gp_c.pyx:24-31) when the factorisation that
+    fails is the dataflow launch (N > 128)."""
+    x = np.linspace(-1.0, 1.0, 700)
+    y = np.sin(x)
+    gp = GP(GaussianKernel(1.0, 1.0), x, y, s=0)
+    assert gp.log_lh == -np.inf and gp.lh == 0 and np.isnan(gp.dloglh_dtheta).all()
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.Lxx
