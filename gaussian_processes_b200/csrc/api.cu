@@ -85,6 +85,7 @@ static GpbOption g_options[] = {
     {"chain_mform", "GPB_CHAIN_MFORM", 0, false},           // M form of the workers' last update(s) of a tile: 0/1 = step j-1, 3, 4 = more (chain.cu build_plan), 2 = off
     {"chain_fuse", "GPB_CHAIN_FUSE", 0, false},             // most backlog steps of a half tile applied by one worker task (default 4)
     {"chain_fuse_guard", "GPB_CHAIN_FUSE_GUARD", 0, false}, // no fused task while a more urgent tile of the group is due within this many steps (default 2, 100 = off)
+    {"stage_overlap", "GPB_STAGE_OVERLAP", 0, false},       // 2 = gpb_gp_stages keeps the triangular solves on the caller's stream
     {"chain_sched", "GPB_CHAIN_SCHED", 0, false},           // workers: 0 = most urgent runnable half tile first, 1 = in-order task lists
     {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = the first chain group of that many CTAs
 };
@@ -682,7 +683,7 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
     gpb_make_kparams(&P, kind, theta, theta[nkp]);
     int stt;
     unsigned done = 0;
-    bool packed = false;
+    bool packed = false, side = false;
     // the read-back block is written by the last kernel straight into page-locked host memory
     // (device-addressable under unified addressing): no copy-engine round trip after the chain
     double* pack_dst = w.pack;
@@ -717,10 +718,23 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
         if (stt) return stt;
         stt = gpb_launch_potrf(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.info, st, n, true, true);
         if (stt) return stt;
-        stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, 0, 0, 1, ypad, 0, w.z, w.alpha, np_, w.flags, st);
+        // The two triangular solves are latency-bound chains of 32 CTAs (2 x 119 us at N = 4096) and touch only L, the
+        // diagonal blocks of W, z and alpha: when the inverse is asked for in the same call they run on a side
+        // stream under the trtri GEMMs and join before the gradient reduction / the read-back.
+        cudaStream_t ss = st;
+        if ((stages & 2u) && np_ >= 1024 && gpb_get_option("stage_overlap") != 2) {
+            stt = gstreams_init();
+            if (stt) return stt;
+            ss = g_gstream[0];
+            GPB_CUDA(cudaEventRecord(g_fork_ev, st));
+            GPB_CUDA(cudaStreamWaitEvent(ss, g_fork_ev, 0));
+            side = true;
+        }
+        stt = gpb_launch_potrs(w.L, w.W, np_, np_, np_, 0, 0, 1, ypad, 0, w.z, w.alpha, np_, w.flags, ss);
         if (stt) return stt;
-        stt = gpb_launch_loglh(w.L, n, np_, 0, 1, ypad, 0, w.alpha, np_, w.info, w.out3, st);
+        stt = gpb_launch_loglh(w.L, n, np_, 0, 1, ypad, 0, w.alpha, np_, w.info, w.out3, ss);
         if (stt) return stt;
+        if (side) GPB_CUDA(cudaEventRecord(g_join_ev[0], ss));
     }
     if (stages & 2u) {          // W = L^-1, V = L^-T
         stt = gpb_launch_trtri(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.Ki, np_, 0, st);
@@ -729,6 +743,10 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
     if (stages & 4u) {          // Ki = V V^T
         stt = gpb_launch_lauum(w.V, np_, np_, 0, 1, w.Ki, np_, 0, st);
         if (stt) return stt;
+    }
+    if (side) {                 // alpha, out3 of the side stream
+        GPB_CUDA(cudaStreamWaitEvent(st, g_join_ev[0], 0));
+        side = false;
     }
     if (stages & 8u) {          // a^T dK_i a, sum(Ki o dK_i), tr Ki, a.a
         const int jsl[3] = {1, 2, 3};

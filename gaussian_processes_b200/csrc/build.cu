@@ -602,9 +602,20 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const double* partial
     }
 }
 
+// CTAs of one matrix's reduction pass = rows of `partial` to provide (capacity; a batched launch uses fewer)
 int gpb_grad_reduce_blocks(long long n) {
-    // four rows per warp (strided, so the triangular row lengths balance): with one row per warp the
-    // block-wide reduction at the end of every CTA cost as much as its 8 rows at N = 1024
+    long long nb = (n + 7) / 8;
+    if (nb > 148 * 4) nb = 148 * 4;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+static int grad_reduce_blocks_used(long long n, bool one_object) {
+    // batches: four rows per warp (strided, so the triangular row lengths balance): with one row per warp the
+    // block-wide reduction at the end of every CTA cost as much as its 8 rows at N = 1024.
+    // One GP object (parameters by value; the batched evaluator passes a parameter array even for one candidate, so
+    // a candidate's sums never depend on how the batch was split): one row per warp -- 128 CTAs left the GPU at 7
+    // warps per SM (136 us at N = 4096, 0.5 TB/s).
+    if (one_object) return gpb_grad_reduce_blocks(n);
     long long nb = (n + 31) / 32;
     if (nb > 148 * 4) nb = 148 * 4;
     if (nb < 1) nb = 1;
@@ -629,7 +640,7 @@ int gpb_launch_grad_reduce(int kind, const KParams* P, const KParams* Pb, int ba
             a.uq[q] = gpb_slice_to_unique(kind, slices[q]);
         }
     }
-    const int nb = gpb_grad_reduce_blocks(n);
+    const int nb = grad_reduce_blocks_used(n, Pb == nullptr && batch == 1);
     dim3 grid((unsigned)nb, 1, (unsigned)batch);
     GpbProfScope prof(GPB_KC_REDUCE, st);
     bool jac = (nsl == gpb_n_kparams(kind));

@@ -77,9 +77,19 @@ __global__ void __launch_bounds__(TileCfg<BM>::THREADS, TileCfg<BM>::MIN_CTAS) g
         diag_tile = (tj == i);
         if (diag_tile && RPG == 2) diag_sub = sub;
     } else {
-        // longest k-range first: for a lower-triangular A the work grows with the row
-        ti = (p.a_tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-        tj = blockIdx.y;
+        // longest k-range first: for a lower-triangular A the work grows with the row, for an upper-triangular one it
+        // shrinks.  The hardware issues CTAs x-fastest, so with a triangular A the row tile is taken from the SLOW
+        // part of the linear CTA index: all column tiles of the longest row first, ... (one matrix, 512 CTAs = 1.7
+        // waves of the last trtri level: the long CTAs of the last columns no longer start in the tail)
+        if (p.a_tri) {
+            const unsigned b = blockIdx.x + gridDim.x * blockIdx.y;
+            ti = (int)(b / gridDim.y);
+            tj = (int)(b % gridDim.y);
+            if (p.a_tri == 1) ti = (int)gridDim.x - 1 - ti;
+        } else {
+            ti = blockIdx.x;
+            tj = blockIdx.y;
+        }
     }
     const int m0 = ti * BM, n0 = tj * BN;
     const long long bz = blockIdx.z / p.nb1, bt = blockIdx.z % p.nb1;
@@ -266,8 +276,15 @@ gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, co
         diag_tile = (tj == i);
         if (diag_tile && RPG == 2) diag_sub = sub;
     } else {
-        ti = (p.a_tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-        tj = blockIdx.y;
+        if (p.a_tri) {
+            const unsigned b = blockIdx.x + gridDim.x * blockIdx.y;
+            ti = (int)(b / gridDim.y);
+            tj = (int)(b % gridDim.y);
+            if (p.a_tri == 1) ti = (int)gridDim.x - 1 - ti;
+        } else {
+            ti = blockIdx.x;
+            tj = blockIdx.y;
+        }
     }
     const int m0 = ti * BM, n0 = tj * BN;
     const long long bz = blockIdx.z / p.nb1, bt = blockIdx.z % p.nb1;
