@@ -486,6 +486,7 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
         a.wclk[v * 4 + 2] = w_upd; a.wclk[v * 4 + 3] = w_n;
     }
     if (!a.mform) return;
+    group_bar(grp);                 // every thread has read the loop's last s_act before it is reused below
     // M-form mode: L(i,j) of this group's TRSMs sits in W's tile (i,j); move it home once the readers of A'(i,j) -- the
     // M-form updates of tiles (i, j+1) and (i, j+2) -- are done.
     for (int tix = 0; tix < nt; tix++) {
