@@ -365,6 +365,12 @@ __device__ __forceinline__ void worker_group(const ChainArgs& a, double* ring, v
 // behind the group's backlog of far-off tiles from step s-1.
 // No deadlock: a group never waits while one of its tasks is runnable, and the globally earliest unfinished task
 // (in step order) always is.
+// L(i,k)[half h] and both halves of L(j,k) final?  (three independent acquire loads)
+__device__ __forceinline__ bool lrh3(const ChainArgs& a, const ChainTile& t, int k) {
+    const int f0 = ld_acquire(f_lrh(a, t.i, t.h, k)), f1 = ld_acquire(f_lrh(a, t.j, 0, k)), f2 = ld_acquire(f_lrh(a, t.j, 1, k));
+    return f0 >= 1 && f1 >= 1 && ((t.i == t.j && t.h == 0) || f2 >= 1);
+}
+
 __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* ring, volatile int* s_act, volatile int* s_task,
                                                  int ltid, int grp) {
     int* err = a.flags;
@@ -402,21 +408,22 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                     const bool l_left = next < (int)my.nupd;
                     // (a tile's updates are applied in step order -- L form 0..nupd-1, then j-2, then j-1 -- whatever the
                     //  timing: the factor is bit-reproducible from run to run)
+                    // (the flags of one task are loaded together: one L2 round trip per poll, not one per flag)
                     if (!l_left && !m2_done) {
-                        if (ld_acquire(f_cnt(a, my.i, my.h, my.j - 2)) >= C_COMPLETE && ld_acquire(f_mp(a, 2, my.j - 2)) >= NH2) cand = 1;
+                        const int f0 = ld_acquire(f_cnt(a, my.i, my.h, my.j - 2)), f1 = ld_acquire(f_mp(a, 2, my.j - 2));
+                        if (f0 >= C_COMPLETE && f1 >= NH2) cand = 1;
                     } else if (!l_left && !m1_done) {
-                        if (ld_acquire(f_cnt(a, my.i, my.h, my.j - 1)) >= C_COMPLETE && ld_acquire(f_mp(a, 1, my.j - 1)) >= NH2) cand = 2;
+                        const int f0 = ld_acquire(f_cnt(a, my.i, my.h, my.j - 1)), f1 = ld_acquire(f_mp(a, 1, my.j - 1));
+                        if (f0 >= C_COMPLETE && f1 >= NH2) cand = 2;
                     } else if (!l_left) {
                         if (ld_acquire(f_diag(a, my.j)) >= 1) cand = 3;
-                    } else if (ld_acquire(f_lrh(a, my.i, my.h, next)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next)) >= 1 &&
-                               ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next)) >= 1)) {
+                    } else if (lrh3(a, my, next)) {
                         cand = 4;
                         // backlog: the following steps too, while their operands are final and live in the same
                         // buffer as this step's (M-form mode: L(r,s) is in W for r >= s + 3, the chain's rows in A)
                         while (nfuse < a.fuse && next + nfuse < (int)my.nupd && (!a.mform || next + nfuse <= my.j - 3) &&
                                (my.dl == dmin || next + nfuse + a.fuse_guard <= dmin) &&
-                               ld_acquire(f_lrh(a, my.i, my.h, next + nfuse)) >= 1 && ld_acquire(f_lrh(a, my.j, 0, next + nfuse)) >= 1 &&
-                               ((my.i == my.j && my.h == 0) || ld_acquire(f_lrh(a, my.j, 1, next + nfuse)) >= 1))
+                               lrh3(a, my, next + nfuse))
                             nfuse++;
                     }
                 }
