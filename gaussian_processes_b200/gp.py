@@ -67,19 +67,17 @@ class memoprop(object):
 
 
 class GP(object):
-    r"""
-    Gaussian Process object.
+    r"""GP regression on fixed observations, every linear-algebra result held on the B200.
 
-    Parameters
-    ----------
-    K : :class:`~gaussian_processes_b200.kernels.Kernel`
-        Kernel object
-    x : numpy.ndarray
-        :math:`n` array of input locations
-    y : numpy.ndarray
-        :math:`n` array of input observations
-    s : number (default=0)
-        Standard deviation of observation noise
+    ``GP(K, x, y, s=0)`` -- same constructor, attributes and memoised properties as the reference's
+    ``gp.GP`` (gp/gp.py:44-127):
+
+    * ``K``: a :class:`~gaussian_processes_b200.kernels.Kernel` (``GaussianKernel``, ``PeriodicKernel``,
+      a ``SymbolicKernel`` or any user subclass);
+    * ``x``, ``y``: the :math:`n` training inputs and targets, 1-D float64 (stored read-only);
+    * ``s``: noise standard deviation added to the diagonal of ``Kxx`` as :math:`s^2`, ``s >= 0``.
+
+    Assigning ``x``, ``y``, ``s``, ``K`` or a parameter drops exactly the cached results that depend on it.
     """
 
     _STATE = ("K", "_x", "_y", "_s", "_memoized")
@@ -388,20 +386,19 @@ class GP(object):
         return self._engine().dm(np.asarray(xo, dtype=DTYPE))
 
     def plot(self, ax=None, xlim=None, color="k", markercolor="r"):
-        """Plot the predictive mean +/- one standard deviation (needs matplotlib)."""
+        """Predictive mean with a one-standard-deviation band over ``xlim`` plus the training points (the picture
+        of gp/gp.py:664-697; needs matplotlib).  The band comes from :meth:`var` -- the diagonal only, the
+        1000 x 1000 covariance the reference forms for it is never built."""
         import matplotlib.pyplot as plt
-        x, y = self._x, self._y
-        if ax is None:
-            ax = plt.gca()
-        if xlim is None:
-            xlim = (x.min(), x.max())
-        X = np.linspace(xlim[0], xlim[1], 1000)
-        mean = self.mean(X)
-        std = np.sqrt(self.var(X))
-        ax.fill_between(X, mean - std, mean + std, color=color, alpha=0.3)
-        ax.plot(X, mean, lw=2, color=color)
-        ax.plot(x, y, "o", ms=5, color=markercolor)
-        ax.set_xlim(*xlim)
+        axes = plt.gca() if ax is None else ax
+        lo, hi = (float(self._x.min()), float(self._x.max())) if xlim is None else xlim
+        grid = np.linspace(lo, hi, 1000)
+        mu = self.mean(grid)
+        sd = np.sqrt(self.var(grid))
+        axes.fill_between(grid, mu - sd, mu + sd, color=color, alpha=0.3)
+        axes.plot(grid, mu, lw=2, color=color)
+        axes.plot(self._x, self._y, "o", ms=5, color=markercolor)
+        axes.set_xlim(lo, hi)
 
     # ------------------------------------------------------------------ batched search (additive)
     def batch_eval(self, thetas, grad=True):
