@@ -267,13 +267,23 @@ class Engine(object):
         for i in range(n_p):
             self.gemv(Ki, n, n, B[i], C[i])
         Kia = self.gemv(Ki, n, n, a)                       # Ki alpha, for the s row
-        Gd = D.empty(nth, nth)
+        # every scalar of this method lands in ONE device block: G | traces | dots -> one read-back at the end
+        # (was 2 n_p + 3 blocking reads; at the reference's own N <= 50 those were the cost of the call)
+        ng, nt_ = nth * nth, nth * nth + 1
+        blk = D.zeros(ng + nt_ + 2 * n_p + 1)
+        Gd = blk[:ng].view(nth, nth)
+        tp = blk[ng:ng + nt_]
+        dots = blk[ng + nt_:]
+
+        def dot_into(u, v, slot):
+            call("gpb_gemv", D.ptr(u), 1, n, n, D.ptr(v), dots[slot:].data_ptr(), 1.0, 0.0, st)
         for i in range(n_p):
             # column over j of b_j . c_i  (the s row/column is assembled from Kia below)
-            call("gpb_gemv", D.ptr(B), n_p, n, npad, D.ptr(C[i]), D.ptr(Gd[i]), 1.0, 0.0, st)
-        bs_ci = [self.dot(a, C[i], n) for i in range(n_p)]           # alpha . c_i
-        bj_kia = [self.dot(B[j], Kia, n) for j in range(n_p)]        # b_j . Ki alpha
-        a_kia = self.dot(a, Kia, n)
+            call("gpb_gemv", D.ptr(B), n_p, n, npad, D.ptr(C[i]), Gd[i].data_ptr(), 1.0, 0.0, st)
+        for i in range(n_p):
+            dot_into(a, C[i], i)                           # alpha . c_i
+            dot_into(B[i], Kia, n_p + i)                   # b_i . Ki alpha
+        dot_into(a, Kia, 2 * n_p)
         # P_i = Ki dK_i (dense products on the DMMA GEMM), then traces of products.  The h-slice of
         # both kernels is proportional to K itself (dK_h = (2/h) K, gaussian_c.pyx:60-69,
         # periodic_c.pyx:65), so P_h = (2/h) (I - s^2 Ki) needs no product: its traces follow from
@@ -284,12 +294,10 @@ class Engine(object):
         P = D.empty(len(dense), npad, npad)
         for q, i in enumerate(dense):
             self.gemm(Ki, J[q], P[q], npad, npad, npad)
-        tp = D.empty(nth * nth + 1)
         part = self._partial()
 
         def trace_prod(A, Bm, slot):
             call("gpb_trace_prod", D.ptr(A), npad, D.ptr(Bm), npad, n, D.ptr(part), tp[slot:].data_ptr(), st)
-        tp.zero_()
         for qi, i in enumerate(dense):
             for qj, j in enumerate(dense):
                 trace_prod(P[qj], P[qi], i * nth + j)
@@ -299,8 +307,10 @@ class Engine(object):
         # Hessian slices: alpha^T H alpha and sum(Ki o H)
         pairs = [(i, j) for i in range(n_p) for j in range(i, n_p)]
         q0, q1, tr, aa = self.slice_reduce([hess_slice(self.kind, i, j) for i, j in pairs])
-        Gh = D.to_host(Gd)
-        tph = D.to_host(tp).copy()
+        blkh = D.to_host(blk).copy()
+        Gh = blkh[:ng].reshape(nth, nth)
+        tph = blkh[ng:ng + nt_]
+        bs_ci, bj_kia, a_kia = blkh[ng + nt_:ng + nt_ + n_p], blkh[ng + nt_ + n_p:ng + nt_ + 2 * n_p], blkh[ng + nt_ + 2 * n_p]
         s2, trKi = s * s, tr
         trKK = tph[nth * nth - 1]
         tph[0 * nth + 0] = ch * ch * (n - 2.0 * s2 * trKi + s2 * s2 * trKK)          # tr(P_h P_h)
@@ -316,10 +326,10 @@ class Engine(object):
             for j in range(n_p):
                 G[i, j] = Gh[i, j]
                 TP[i, j] = tph[i * nth + j]
-            G[i, n_p] = 2 * s * float(bs_ci[i].item())          # b_s . c_i
-            G[n_p, i] = 2 * s * float(bj_kia[i].item())         # b_i . c_s
+            G[i, n_p] = 2 * s * float(bs_ci[i])                 # b_s . c_i
+            G[n_p, i] = 2 * s * float(bj_kia[i])                # b_i . c_s
             TP[i, n_p] = TP[n_p, i] = 2 * s * tph[i * nth + n_p]
-        G[n_p, n_p] = 4 * s * s * float(a_kia.item())
+        G[n_p, n_p] = 4 * s * s * float(a_kia)
         TP[n_p, n_p] = 4 * s * s * tph[nth * nth - 1]
         for (i, j), v0, v1 in zip(pairs, q0, q1):
             Q[i, j] = Q[j, i] = v0
