@@ -47,9 +47,13 @@ namespace {
 
 constexpr int CT = GPB_NB;                  // tile edge
 constexpr int HR = 64;                      // rows of a half tile
-constexpr int CBK = 16;                     // k-chunk of the ring
+#ifndef GPB_CBK
+#define GPB_CBK 16
+#define GPB_GSTAGES 3
+#endif
+constexpr int CBK = GPB_CBK;                // k-chunk of the ring
 constexpr int CLD = CBK + 4;                // padded row stride (doubles): conflict-free 8-byte fragment loads
-constexpr int GSTAGES = 3;
+constexpr int GSTAGES = GPB_GSTAGES;
 constexpr int CTHREADS = 512;
 constexpr int GTHREADS = 256;               // one worker group
 constexpr int G_A = HR * CLD, G_B = CT * CLD, G_STAGE = G_A + G_B;      // doubles
@@ -146,9 +150,10 @@ __device__ __forceinline__ void group_bar(int grp) {
 template <int ROWS>
 __device__ __forceinline__ void ring_load(double* sdst, const double* g, long long ld, int ltid) {
 #pragma unroll
-    for (int q = 0; q < ROWS * 8 / GTHREADS; q++) {
+    constexpr int PPR = CBK / 2;            // 16-byte pieces per row
+    for (int q = 0; q < ROWS * PPR / GTHREADS; q++) {
         const int c = ltid + q * GTHREADS;
-        const int row = c >> 3, ch = c & 7;
+        const int row = c / PPR, ch = c % PPR;
         cp_async16(sdst + row * CLD + ch * 2, g + (long long)row * ld + ch * 2);
     }
 }
@@ -215,7 +220,7 @@ __device__ __forceinline__ void task_trsm(const ChainArgs& a, int i, int h, int 
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    half_mm(acc, At, a.ld, Wk, a.ldw, wm, wn, (wn + 1) * 2, ring, ltid, grp);
+    half_mm(acc, At, a.ld, Wk, a.ldw, wm, wn, (wn + 1) * 32 / CBK, ring, ltid, grp);
     // every thread's loads of the half tile are complete (barrier at the end of half_mm): safe to overwrite
     long long ldd;
     double* Dt = const_cast<double*>(l_tile(a, i, k, ldd)) + (long long)h * HR * ldd;
