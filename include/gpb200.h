@@ -267,9 +267,16 @@ int64_t gpb_launch_count(void);
  *   "potrf_inner"  (GPB_POTRF_INNER)  128-columns per outer Cholesky panel
  *   "potrf_lookahead" (GPB_POTRF_LOOKAHEAD) panel look-ahead of a single factorisation: 0 auto (N >= 6144), 1 on, 2 off
  *   "gemm_impl"    (GPB_GEMM_IMPL)    0 TMA + mbarrier operand pipeline, 1 cp.async pipeline
- *   "potrf_dataflow" (GPB_POTRF_DATAFLOW) one matrix by the persistent dataflow launch: 0 auto (256 <= N <= 6144), 1 whenever batch == 1, 2 never
- *   "chain_group"  (GPB_CHAIN_GROUP)  CTAs sharing the dataflow factorisation's critical path: 8 (default) or 4
- *   "chain_diag"   (GPB_CHAIN_DIAG)   2 = the chain CTA factors diagonal blocks with the 256-thread body              */
+ *   "potrf_dataflow" (GPB_POTRF_DATAFLOW) one matrix by the persistent dataflow launch: 0 auto (256 <= N <= 8192), 1 whenever batch == 1, 2 never
+ *   "chain_group"  (GPB_CHAIN_GROUP)  0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = the first
+ *                                     chain group of that many CTAs (TRSM + SYRK of the chain tiles after the diagonal block)
+ *   "chain_diag"   (GPB_CHAIN_DIAG)   2 = the chain CTA factors diagonal blocks with the 256-thread body
+ *   "chain_sched"  (GPB_CHAIN_SCHED)  workers: 0 = most urgent runnable half tile first, 1 = in-order task lists
+ *   "chain_mform"  (GPB_CHAIN_MFORM)  M form of a tile's last worker update(s): 0/1 = last step, 3 / 4 = more, 2 = off
+ *   "chain_fuse"   (GPB_CHAIN_FUSE)   most backlog steps of a half tile applied by one worker task (default 4)
+ *   "chain_fuse_guard", "chain_express"  scheduling experiments (csrc/chain.cu)
+ *   "stage_overlap" (GPB_STAGE_OVERLAP) 2 = gpb_gp_stages keeps the triangular solves on the caller's stream
+ * None of them changes a result beyond rounding; the dataflow variants are compared in tests/test_parity_gpu_r2.py. */
 int gpb_set_option(const char* name, int value);
 /* Per-kernel-class device timing: while enabled, each launch group of a class is bracketed
  * by CUDA events on its stream.  Classes: 0 DMMA GEMM, 1 diagonal-block factor, 2 kernel
