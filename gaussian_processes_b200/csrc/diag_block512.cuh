@@ -167,23 +167,48 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
     __syncthreads();
     D512_STAMP(1);
 
+    // (both copies read eight elements before they store them: one warp's dependent load -> store pairs cost ~60
+    //  cycles each, 4 k cycles for the 32x32 W / V block, and the release fence then waits for the stores)
     auto store_Lcol = [&](int cb, int first, int nthr) {
         for (int bi = cb; bi < 4; bi++) {
             const double* ls = Lb + blk(bi, cb) * SBSZ;
             const int stride = (bi == cb) ? DLD : SLD;
-            for (int e = first; e < SB * SB; e += nthr) {
-                const int r = e >> 5, c = e & 31;
-                A[(long long)(bi * SB + r) * ld + cb * SB + c] = ls[r * stride + c];
+            double* dst = A + (long long)(bi * SB) * ld + cb * SB;
+            for (int e0 = first; e0 < SB * SB; e0 += nthr * 8) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int e = e0 + q * nthr;
+                    v[q] = (e < SB * SB) ? ls[(e >> 5) * stride + (e & 31)] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int e = e0 + q * nthr;
+                    if (e < SB * SB) dst[(long long)(e >> 5) * ld + (e & 31)] = v[q];
+                }
             }
         }
     };
     auto store_Wdiag = [&](int cb, int first, int nthr) {
         const double* ws = Wd + cb * SBSZ;
-        for (int e = first; e < SB * SB; e += nthr) {
-            const int r = e >> 5, c = e & 31;
-            const long long gr = cb * SB + r, gc = cb * SB + c;
-            W[gr * ldw + gc] = ws[r * SLD + c];
-            if (V) V[gr * ldv + gc] = ws[c * SLD + r];
+        double* wdst = W + (long long)(cb * SB) * ldw + cb * SB;
+        double* vdst = V ? V + (long long)(cb * SB) * ldv + cb * SB : nullptr;
+        for (int e0 = first; e0 < SB * SB; e0 += nthr * 8) {
+            double v[8], u[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int e = e0 + q * nthr, r = e >> 5, c = e & 31;
+                v[q] = (e < SB * SB) ? ws[r * SLD + c] : 0.0;
+                u[q] = (e < SB * SB && vdst) ? ws[c * SLD + r] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int e = e0 + q * nthr, r = e >> 5, c = e & 31;
+                if (e < SB * SB) {
+                    wdst[(long long)r * ldw + c] = v[q];
+                    if (vdst) vdst[(long long)r * ldv + c] = u[q];
+                }
+            }
         }
     };
 
@@ -209,6 +234,12 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
         if (dclk && ph == 3 && tid == 0) dclk[26] = clock64();
         int nst = 0;                                             // strips this warp runs at the end of the phase
         bool pair_sync = false;                                  // two dependent strips of a warp pair (W_10)
+        if (lpub && wid == 15 && lane == 0 && (ph == 3 || ph == 5 || ph == 7)) {
+            // block column (ph - 3) / 2 of L and its inverted diagonal block were stored in the previous phase (the
+            // phase barrier ordered those stores before this fence)
+            __threadfence();
+            st_release(lpub + (ph - 3) / 2, 1);
+        }
         if (is_s) {
             double* invb = invd + (bb & 3) * SB;
             if (wid == 0) {
@@ -272,11 +303,12 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                     if (fail && lane == 0 && *info == 0) *info = col0 + bb * SB + fail;
                 }
             } else if (wid <= 3) {
-                if (bb < 4 && wid <= 3 - bb) {
-                    // ---- rows below, block (bb + wid, bb): X = A L_bb^-T through the column stream (lane = row):
+                if (bb < 4 && wid > bb) {
+                    // ---- rows below, block (wid, bb): X = A L_bb^-T through the column stream (lane = row):
                     //      x_l = a_l / L_ll, then a_c -= x_l L_cl for c > l -- the same right-looking step the
-                    //      sweep applies to its own rows, one column behind it
-                    const int bi = bb + wid;
+                    //      sweep applies to its own rows, one column behind it.  (Block row = warp index: from S1 on
+                    //      warp 1 is free, so the 32x32 inverse of warp 5 has their shared sub-partition to itself.)
+                    const int bi = wid;
                     double* Ab = Lb + blk(bi, bb) * SBSZ;
                     double* St = Wd + bi * SBSZ;              // private staging (this inverse slot is still unused)
                     for (int r = 0; r < SB; r++) St[r * DLD + lane] = Ab[r * SLD + lane];
@@ -313,28 +345,93 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                 }
             } else if (wid == 5) {
                 if (bb > 0) {
-                    // ---- inverse of the previous 32x32 factor: lane c solves L w = e_c (rows of L broadcast)
-                    const double* Lp = Lb + blk(bb - 1, bb - 1) * SBSZ;
+                    // ---- inverse of the previous 32x32 factor, two levels: both 16x16 diagonal blocks at once by forward
+                    //      substitution (lanes 0-15: column cc of W_11 from L_11, lanes 16-31: of W_22 from L_22; 120 FMAs
+                    //      per lane), then W_21 = -W_22 (L_21 W_11) as two 16x16x16 DMMA products.  (The 32-row substitution
+                    //      -- 496 dependent-ish FMAs of straight-line code per lane -- took 10-15 k cycles and was the last
+                    //      warp of every sweep phase.)
+                    const double* Lp = Lb + blk(bb - 1, bb - 1) * SBSZ;       // stride DLD
                     const double* ip = invd + (bb - 1) * SB;
-                    double w[SB];
+                    double* Wo = Wd + (bb - 1) * SBSZ;                        // stride SLD
+                    const int hi = lane >> 4, cc = lane & 15;
+                    if (dclk && lane == 0) dclk[200 + ph * 6 + 0] = clock64();
+                    const double* Lh = Lp + (hi * 16) * DLD + hi * 16;
+                    double w[16];
 #pragma unroll
-                    for (int r = 0; r < SB; r++) {
+                    for (int r = 0; r < 16; r++) {
                         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                         for (int k = 0; k + 1 < r; k += 2) {
-                            s0 = fma(Lp[r * DLD + k], w[k], s0);
-                            s1 = fma(Lp[r * DLD + k + 1], w[k + 1], s1);
+                            s0 = fma(Lh[r * DLD + k], w[k], s0);
+                            s1 = fma(Lh[r * DLD + k + 1], w[k + 1], s1);
                         }
-                        if (r & 1) s0 = fma(Lp[r * DLD + r - 1], w[r - 1], s0);
-                        w[r] = (((r == lane) ? 1.0 : 0.0) - (s0 + s1)) * ip[r];
+                        if (r & 1) s0 = fma(Lh[r * DLD + r - 1], w[r - 1], s0);
+                        w[r] = (((r == cc) ? 1.0 : 0.0) - (s0 + s1)) * ip[hi * 16 + r];
                     }
-                    double* Wo = Wd + (bb - 1) * SBSZ;
 #pragma unroll
-                    for (int r = 0; r < SB; r++) Wo[r * SLD + lane] = w[r];
+                    for (int r = 0; r < 16; r++) Wo[(hi * 16 + r) * SLD + lane] = w[r];
+                    __syncwarp();
+                    if (dclk && lane == 0) dclk[200 + ph * 6 + 1] = clock64();
+                    {
+                        const int g = lane >> 2, t = lane & 3;
+                        double* Tt = Wo + 16;                                  // scratch: the (zero) block W_12
+                        // T = L_21 W_11   (W_11 lower triangular: k >= column; all 16 k are walked, the zeros are stored)
+                        double c[2][2][2];
+#pragma unroll
+                        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+                            for (int tj = 0; tj < 2; tj++) c[ti][tj][0] = c[ti][tj][1] = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            double av[2], bv[2];
+#pragma unroll
+                            for (int ti = 0; ti < 2; ti++) av[ti] = Lp[(16 + ti * 8 + g) * DLD + kk * 4 + t];
+#pragma unroll
+                            for (int tj = 0; tj < 2; tj++) bv[tj] = Wo[(kk * 4 + t) * SLD + tj * 8 + g];
+#pragma unroll
+                            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+                                for (int tj = 0; tj < 2; tj++) dmma884(c[ti][tj][0], c[ti][tj][1], av[ti], bv[tj]);
+                        }
+#pragma unroll
+                        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+                            for (int tj = 0; tj < 2; tj++) {
+                                Tt[(ti * 8 + g) * SLD + tj * 8 + 2 * t] = c[ti][tj][0];
+                                Tt[(ti * 8 + g) * SLD + tj * 8 + 2 * t + 1] = c[ti][tj][1];
+                                c[ti][tj][0] = c[ti][tj][1] = 0.0;
+                            }
+                        __syncwarp();
+                        // W_21 = -W_22 T
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            double av[2], bv[2];
+#pragma unroll
+                            for (int ti = 0; ti < 2; ti++) av[ti] = -Wo[(16 + ti * 8 + g) * SLD + 16 + kk * 4 + t];
+#pragma unroll
+                            for (int tj = 0; tj < 2; tj++) bv[tj] = Tt[(kk * 4 + t) * SLD + tj * 8 + g];
+#pragma unroll
+                            for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+                                for (int tj = 0; tj < 2; tj++) dmma884(c[ti][tj][0], c[ti][tj][1], av[ti], bv[tj]);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+                            for (int tj = 0; tj < 2; tj++) {
+                                Wo[(16 + ti * 8 + g) * SLD + tj * 8 + 2 * t] = c[ti][tj][0];
+                                Wo[(16 + ti * 8 + g) * SLD + tj * 8 + 2 * t + 1] = c[ti][tj][1];
+                                Tt[(ti * 8 + g) * SLD + tj * 8 + 2 * t] = 0.0;
+                                Tt[(ti * 8 + g) * SLD + tj * 8 + 2 * t + 1] = 0.0;
+                            }
+                    }
+                    if (dclk && lane == 0) dclk[200 + ph * 6 + 2] = clock64();
                     if (lpub) {
                         __syncwarp();
                         store_Wdiag(bb - 1, lane, 32);
                     }
+                    if (dclk && lane == 0) dclk[200 + ph * 6 + 3] = clock64();
                 }
             } else if (wid == 6 || wid == 7) {
                 if (bb > 0) store_Lcol(bb - 1, tid - 6 * 32, 64);      // previous L column -> global
@@ -365,16 +462,20 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                     pair_sync = true;
                 }
             }
-            if (lpub && bb > 0 && wid >= 5 && wid <= 7) {
-                // block column bb-1 of L (warps 6, 7) and its inverted diagonal block (warp 5) are stored: publish.
+            if (lpub && bb == 4 && wid >= 5 && wid <= 7) {
+                // last block column of L (warps 6, 7) and its inverted diagonal block (warp 5) are stored: publish.
                 // (ONE barrier instruction for the three warps: synccheck rejects a named barrier whose
-                //  participants arrive from different instructions)
+                //  participants arrive from different instructions.)  Columns 0..2 are released by warp 15 at the
+                // start of the NEXT phase instead: the release fence waits 2-5 k cycles for the stores to be
+                // acknowledged, and inside the sweep phase that made warp 5 the last warp at every phase barrier.
                 __syncwarp();
                 asm volatile("bar.sync 6, 96;\n" ::: "memory");
+                if (dclk && wid == 5 && lane == 0) dclk[200 + ph * 6 + 4] = clock64();
                 if (wid == 5 && lane == 0) {
                     __threadfence();
                     st_release(lpub + (bb - 1), 1);
                 }
+                if (dclk && wid == 5 && lane == 0) dclk[200 + ph * 6 + 5] = clock64();
             }
             if (bb == 4 && !lpub) {
                 // S(4): S_32 = L_32 W_22 (warps 9, 10) and S_ij = sum_k L_ik W_kj, i = 2,3; j = 0,1 (eight strips)

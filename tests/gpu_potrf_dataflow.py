@@ -82,6 +82,9 @@ arr = w[328:368].reshape(-1)[:160].reshape(10, 16) - dc[0]
 names = ["S0", "C0", "S1", "C1", "S2", "C2", "S3", "T1", "T2", "T3"]
 for ph in range(10):
     print("  %s warp arrivals (cycles since block start):" % names[ph], arr[ph].tolist())
+w5 = w.reshape(-1)[1280 + 200:1280 + 248].reshape(8, 6) - dc[0]
+for ph in (2, 4, 6, 7):
+    print("  warp 5 in phase %d (cycles since block start): start %d | substitution done %d | products done %d | W block stored %d | barrier with the L-column warps %d | released %d" % ((ph,) + tuple(w5[ph].tolist())))
 hc = w[(1280 + 256) // 4:(1280 + 256 + 8 * T) // 4].reshape(-1)[:8 * T].reshape(T, 8)
 kk = min(T - 2, max(2, T // 2))
 print("helper 0 waits per step (cycles): urgent inputs", (hc[2:, 1] - hc[2:, 0]).tolist())
