@@ -290,7 +290,10 @@ __device__ __forceinline__ void publish_group(int* flag, int value, int ltid, in
 
 __device__ __forceinline__ void worker_group(const ChainArgs& a, double* ring, volatile int* s_act, int ltid, int grp) {
     int* err = a.flags;
-    const int v = ((int)blockIdx.x - a.NG) * 2 + grp;          // worker group index
+    // worker group index: consecutive indices sit on DIFFERENT SMs (the plan deals the two halves of a tile to
+    // consecutive groups; as siblings on one SM the two halves of an urgent tile ran at half speed each, 25 us
+    // instead of 12, while most other SMs were idle)
+    const int v = grp * ((int)gridDim.x - a.NG) + ((int)blockIdx.x - a.NG);
     int bt = a.bulk_off[v];
     const int bend = a.bulk_off[v + 1];
     int qt = a.trsm_off[v];
@@ -379,7 +382,10 @@ __device__ __forceinline__ bool lrh3(const ChainArgs& a, const ChainTile& t, int
 __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* ring, volatile int* s_act, volatile int* s_task,
                                                  int ltid, int grp) {
     int* err = a.flags;
-    const int v = ((int)blockIdx.x - a.NG) * 2 + grp;          // worker group index
+    // worker group index: consecutive indices sit on DIFFERENT SMs (the plan deals the two halves of a tile to
+    // consecutive groups; as siblings on one SM the two halves of an urgent tile ran at half speed each, 25 us
+    // instead of 12, while most other SMs were idle)
+    const int v = grp * ((int)gridDim.x - a.NG) + ((int)blockIdx.x - a.NG);
     const int t0 = a.tile_off[v], nt = a.tile_off[v + 1] - t0;
     ChainTile my = {0, 0, 0, 0, 0, 0, 0, 0};
     int next = 0;                  // L-form updates applied (steps 0..next-1)
