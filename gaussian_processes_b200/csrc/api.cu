@@ -86,6 +86,8 @@ static GpbOption g_options[] = {
     {"chain_fuse", "GPB_CHAIN_FUSE", 0, false},             // most backlog steps of a half tile applied by one worker task (default 4)
     {"chain_fuse_guard", "GPB_CHAIN_FUSE_GUARD", 0, false}, // no fused task while a more urgent tile of the group is due within this many steps (default 2, 100 = off)
     {"stage_overlap", "GPB_STAGE_OVERLAP", 0, false},       // 2 = gpb_gp_stages keeps the triangular solves on the caller's stream
+    {"chain_horizon", "GPB_CHAIN_HORIZON", 0, false},       // far tiles (deadline > step + horizon) yield while their group has an imminent tile (default 3, 100 = off)
+    {"chain_imminent", "GPB_CHAIN_IMMINENT", 0, false},     // ... "imminent": due within this many steps (default 1)
     {"chain_sched", "GPB_CHAIN_SCHED", 0, false},           // workers: 0 = most urgent runnable half tile first, 1 = in-order task lists
     {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = the first chain group of that many CTAs
 };

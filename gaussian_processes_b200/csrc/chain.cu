@@ -87,6 +87,8 @@ struct ChainArgs {
     int NG;                     // CTAs of the chain group (CTA 0 = the chain, 1..NG-1 its helpers)
     int diag512;                // 1: full diagonal blocks by the 512-thread body (diag_block512.cuh)
     int pipelined;              // 1: chain group v2 (c0 publishes every 32-column block; helpers one block behind; inverter CTA)
+    int imminent;               // "due soon": deadline <= step + imminent
+    int horizon;                // a far tile (deadline > step + horizon) yields while the group has an imminent tile
     int fuse_guard;             // ... unless a more urgent tile of the group is due within this many steps
     int fuse;                   // most steps of one half tile's backlog applied in one task (K = 128 * steps)
     int mform;                  // 1: last worker update of a tile in M form, worker TRSMs out of place (see worker_group_edf)
@@ -389,6 +391,7 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
     const int t0 = a.tile_off[v], nt = a.tile_off[v + 1] - t0;
     ChainTile my = {0, 0, 0, 0, 0, 0, 0, 0};
     int next = 0;                  // L-form updates applied (steps 0..next-1)
+    int s_cur = 0;                 // diagonal blocks known to be published
     bool m1_done = true, m2_done = true;   // the M-form updates of steps j-1 (has_m bit 0) and j-2 (bit 1) applied, or none
     bool live = false;
     if (ltid < 32 && ltid < nt) {
@@ -415,6 +418,8 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                 // the group's most urgent live tile: a long fused task must not start when that tile's last updates
                 // are about to become runnable (tasks are not preempted)
                 const int dmin = (int)__reduce_min_sync(0xffffffffu, live ? (unsigned)my.dl : 0x7fffffffu);
+                // how far the factorisation is (diagonal blocks published; at most one step per poll round)
+                if (s_cur < a.T && ld_acquire(f_diag(a, s_cur)) >= 1) s_cur++;
                 if (live) {
                     const bool l_left = next < (int)my.nupd;
                     // (a tile's updates are applied in step order -- L form 0..nupd-1, then j-2, then j-1 -- whatever the
@@ -428,6 +433,11 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                         if (f0 >= C_COMPLETE && f1 >= NH2) cand = 2;
                     } else if (!l_left) {
                         if (ld_acquire(f_diag(a, my.j)) >= 1) cand = 3;
+                    } else if (my.dl != dmin && dmin <= s_cur + a.imminent && my.dl > s_cur + a.horizon) {
+                        // Tasks are not preempted: while the group's most urgent tile is due within a step, a tile
+                        // that is not needed for `horizon` more steps waits (its backlog is absorbed -- fused -- in the
+                        // second half of the factorisation, where the workers have time).  Everything an imminent task
+                        // depends on has a deadline <= its own, so nothing it waits for is ever held back here.
                     } else if (lrh3(a, my, next)) {
                         cand = 4;
                         // backlog: the following steps too, while their operands are final and live in the same
@@ -1362,6 +1372,11 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     a.tclk = reinterpret_cast<long long*>(a.M + (size_t)3 * T * CT * CT);
     a.mform = a.tiles ? mform : 0;
     a.fuse = gpb_get_option("chain_fuse");            // 0 -> default
+    a.imminent = gpb_get_option("chain_imminent");
+    if (a.imminent <= 0) a.imminent = 1;
+    a.horizon = gpb_get_option("chain_horizon");          // 0 -> default; 100 = off
+    if (a.horizon <= 0) a.horizon = 3;
+    if (a.horizon >= 100) a.horizon = 1 << 20;
     a.fuse_guard = gpb_get_option("chain_fuse_guard");
     if (a.fuse_guard <= 0) a.fuse_guard = 2;
     if (a.fuse_guard >= 100) a.fuse_guard = -1000;       // (off)
@@ -1462,7 +1477,7 @@ extern "C" int gpb_debug_tile_bench(double* A, long long ld, double* W, long lon
         attr_set = true;
     }
     ChainArgs a;
-    a.tiles = nullptr; a.tile_off = nullptr; a.mform = 0; a.fuse = 1; a.fuse_guard = 2; a.M = nullptr; a.tclk = nullptr;
+    a.tiles = nullptr; a.tile_off = nullptr; a.mform = 0; a.fuse = 1; a.fuse_guard = 2; a.horizon = 1 << 20; a.imminent = 1; a.M = nullptr; a.tclk = nullptr;
     a.A = A; a.ld = ld; a.W = W; a.ldw = ldw; a.V = nullptr; a.ldv = 0; a.info = nullptr; a.T = 3; a.n_valid = 0;
     a.NG = 8; a.pipelined = 0; a.diag512 = 1; a.flags = flags; a.bulk = nullptr; a.bulk_off = nullptr; a.trsm = nullptr; a.trsm_off = nullptr;
     a.clk = nullptr; a.wclk = nullptr;

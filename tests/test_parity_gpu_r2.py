@@ -397,6 +397,7 @@ DATAFLOW_VARIANTS = [
     {"chain_mform": 2}, {"chain_mform": 3}, {"chain_mform": 4},
     {"chain_fuse": 1}, {"chain_fuse": 8, "chain_fuse_guard": 100},
     {"chain_group": 8}, {"chain_group": 4}, {"chain_sched": 1, "chain_express": 1},
+    {"chain_horizon": 100}, {"chain_horizon": 1, "chain_imminent": 3},
 ]
 
 
