@@ -88,6 +88,8 @@ static GpbOption g_options[] = {
     {"stage_overlap", "GPB_STAGE_OVERLAP", 0, false},       // 2 = gpb_gp_stages keeps the triangular solves on the caller's stream
     {"chain_horizon", "GPB_CHAIN_HORIZON", 0, false},       // far tiles (deadline > step + horizon) yield while their group has an imminent tile (default 3, 100 = off)
     {"chain_imminent", "GPB_CHAIN_IMMINENT", 0, false},     // ... "imminent": due within this many steps (default 1)
+    {"chain_band", "GPB_CHAIN_BAND", 0, false},             // SMs dedicated to the tiles next to the diagonal (1 = off)
+    {"chain_band_x", "GPB_CHAIN_BAND_X", 0, false},         // L-form steps of a band tile taken over by its band group (default 2)
     {"chain_sched", "GPB_CHAIN_SCHED", 0, false},           // workers: 0 = most urgent runnable half tile first, 1 = in-order task lists
     {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = the first chain group of that many CTAs
 };

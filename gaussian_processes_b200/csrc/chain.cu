@@ -76,7 +76,10 @@ struct ChainTask { unsigned char type, h; short i, j, k; };
 // One half tile owned by a worker group (scheduler 0): it receives the updates of steps 0..nupd-1 from its owner,
 // then (has_trsm) the owner's TRSM at step j.  (The last one or two steps of the tiles next to the diagonal belong to
 // the chain group.)
-struct ChainTile { short i, j; unsigned char h, nupd, has_trsm, has_m; short dl, pad; };    // dl: step that consumes the finished tile
+// dl: step that consumes the finished tile.  start / handoff: a tile of the diagonal band is owned by a regular group for
+// its steps [0, nupd) (handoff = 1: that entry publishes its count, never "complete") and by a band group -- alone on its
+// SM -- from step `start` on (it waits for CNT >= start first).
+struct ChainTile { short i, j; unsigned char h, nupd, has_trsm, has_m; short dl; unsigned char start, handoff; };
 
 struct ChainArgs {
     double* A; long long ld;
@@ -389,18 +392,21 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
     // instead of 12, while most other SMs were idle)
     const int v = grp * ((int)gridDim.x - a.NG) + ((int)blockIdx.x - a.NG);
     const int t0 = a.tile_off[v], nt = a.tile_off[v + 1] - t0;
-    ChainTile my = {0, 0, 0, 0, 0, 0, 0, 0};
+    ChainTile my = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int next = 0;                  // L-form updates applied (steps 0..next-1)
     int s_cur = 0;                 // diagonal blocks known to be published
     bool m1_done = true, m2_done = true;   // the M-form updates of steps j-1 (has_m bit 0) and j-2 (bit 1) applied, or none
     bool live = false;
+    bool handed = true;            // (band group) the regular owner has applied its part of the tile
     if (ltid < 32 && ltid < nt) {
         my = a.tiles[t0 + ltid];
         m1_done = !(my.has_m & 1);
         m2_done = !(my.has_m & 2);
-        live = (my.nupd > 0) || my.has_m || my.has_trsm;
+        next = my.start;
+        handed = my.start == 0;
+        live = (my.nupd > next) || my.has_m || my.has_trsm;
         // nothing to receive: complete from the start (the M-form readers of this tile poll it)
-        if (my.nupd == 0 && !my.has_m) st_release(f_cnt(a, my.i, my.h, my.j), C_COMPLETE);
+        if (my.nupd == 0 && !my.has_m && !my.handoff) st_release(f_cnt(a, my.i, my.h, my.j), C_COMPLETE);
     }
     long long w_wait = 0, w_trsm = 0, w_upd = 0, w_n = 0;
     for (;;) {
@@ -415,12 +421,13 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                 // M_{j,kappa} published), 3 = TRSM (nothing else left, DIAG[j]), 4 = L-form update of step `next`
                 int cand = 0;
                 nfuse = 1;
+                if (live && !handed && ld_acquire(f_cnt(a, my.i, my.h, my.j)) >= (int)my.start) handed = true;
                 // the group's most urgent live tile: a long fused task must not start when that tile's last updates
                 // are about to become runnable (tasks are not preempted)
                 const int dmin = (int)__reduce_min_sync(0xffffffffu, live ? (unsigned)my.dl : 0x7fffffffu);
                 // how far the factorisation is (diagonal blocks published; at most one step per poll round)
                 if (s_cur < a.T && ld_acquire(f_diag(a, s_cur)) >= 1) s_cur++;
-                if (live) {
+                if (live && handed) {
                     const bool l_left = next < (int)my.nupd;
                     // (a tile's updates are applied in step order -- L form 0..nupd-1, then j-2, then j-1 -- whatever the
                     //  timing: the factor is bit-reproducible from run to run)
@@ -477,7 +484,7 @@ __device__ __forceinline__ void worker_group_edf(const ChainArgs& a, double* rin
                 s_task[grp * 6 + 1] = ((int)my.i << 16) | (int)my.j;
                 s_task[grp * 6 + 2] = (int)my.h;
                 s_task[grp * 6 + 3] = k;
-                s_task[grp * 6 + 4] = complete ? C_COMPLETE : next;
+                s_task[grp * 6 + 4] = (complete && !my.handoff) ? C_COMPLETE : next;
                 s_task[grp * 6 + 5] = (type == TASK_UPD) ? nfuse : 1;
             }
             if (lane == 0) s_act[grp] = act;
@@ -1153,14 +1160,17 @@ std::map<cudaStream_t, std::pair<int*, size_t>> g_flag_pool;
 std::map<cudaStream_t, int> g_last_T;
 std::mutex g_plan_mu;
 
-int build_plan(int T, int G, int NG, int mform, ChainPlan* out) {
+int build_plan(int T, int G, int NG, int mform, int band, ChainPlan* out) {
     const bool pipelined = (NG == NH2 + 2);
     const bool express = gpb_get_option("chain_express") == 1;
-    NG += 1000 * mform;              // (plan cache key only)
+    int band_x = gpb_get_option("chain_band_x");
+    if (band_x <= 0) band_x = 2;
+    NG += 1000 * mform + 10000 * band + 1000000 * band_x;              // (plan cache key only)
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto it = g_plans.find({{T, G}, NG + (express ? 100 : 0)});
     if (it != g_plans.end()) { *out = it->second; return GPB_OK; }
     const int nv = 2 * (G - NG % 1000);     // worker groups
+    const int nW = nv / 2;                   // worker CTAs; group index v = grp * nW + cta (see worker_group_edf)
     // pipelined group: worker groups 0..3 are EXPRESS groups.  Per step s they run exactly the tasks the chain group
     // waits for one step later -- TRSM(s+3, s) and the step-s updates of tiles (s+3, s+1), (s+3, s+2), (s+3, s+3) -- and
     // nothing else, so those tasks never queue behind a regular group's 20-40 k-cycle backlog.
@@ -1232,6 +1242,21 @@ int build_plan(int T, int G, int NG, int mform, ChainPlan* out) {
         std::vector<int> off(nv + 1, 0);
         std::vector<std::vector<ChainTile>> tl(nv);
         size_t most = 0;
+        // band groups: group 0 of the first `band` worker CTAs (their group 1 stays empty); owner() deals over the rest
+        std::vector<int> regular;
+        for (int g = 0; g < nv; g++)
+            if (!(band > 0 && (g % nW) < band)) regular.push_back(g);
+        if (band > 0) {
+            long long n = 0;
+            const int nreg = (int)regular.size();
+            for (int j = T - 1; j >= 0; j--)
+                for (int i = j; i < T; i++)
+                    for (int h = 0; h < 2; h++) {
+                        const long long round = n / nreg, pos = n % nreg;
+                        own[((size_t)2 * i + h) * T + j] = (int)((round & 1) ? nreg - 1 - pos : pos);
+                        n++;
+                    }
+        }
         // a tile's deadline = the step that consumes its last worker-side update: column j for most, one or two
         // steps earlier for the tiles the chain group finishes itself
         std::vector<std::pair<std::pair<int, int>, std::pair<int, int>>> order;       // ((deadline, j), (i, h))
@@ -1244,6 +1269,7 @@ int build_plan(int T, int G, int NG, int mform, ChainPlan* out) {
                     order.push_back({{dl, j}, {i, h}});
                 }
         std::sort(order.begin(), order.end());
+        long long band_next = 0;          // band tiles are dealt round-robin in deadline order: every step's finishing tiles spread over all band groups
         for (auto& o : order) {
             const int j = o.first.second, i = o.second.first, h = o.second.second;
             int nupd = j, has_trsm, has_m = 0;
@@ -1270,9 +1296,27 @@ int build_plan(int T, int G, int NG, int mform, ChainPlan* out) {
                 if (i == j) nupd = j - 1;
             }
             if (nupd < 0) nupd = 0;
-            auto& l = tl[owner(i, h, j)];
+            const int dl = o.first.first < 0 ? 0 : o.first.first;
+            if (band > 0 && i - j <= 3) {
+                // Diagonal band (tiles (k,k) ... (k,k-3): everything the helpers' urgent phase reads, plus the TRSM of
+                // row k-3+3 that feeds it).  The regular owner applies all but the last band_x L-form steps and hands the
+                // tile over; a band group -- alone on its SM, so a task takes 12 us instead of 23 and never queues behind
+                // a backlog task -- applies the rest, the M-form step and the TRSM.
+                const int R = nupd > band_x ? nupd - band_x : 0;
+                if (R > 0) {
+                    auto& l = tl[regular[owner(i, h, j)]];
+                    l.push_back({(short)i, (short)j, (unsigned char)h, (unsigned char)R, 0, 0, (short)(dl > band_x ? dl - band_x : 0), 0, 1});
+                    if (l.size() > most) most = l.size();
+                }
+                auto& l = tl[(band_next++) % band];
+                l.push_back({(short)i, (short)j, (unsigned char)h, (unsigned char)nupd, (unsigned char)has_trsm, (unsigned char)has_m,
+                             (short)dl, (unsigned char)R, 0});
+                if (l.size() > most) most = l.size();
+                continue;
+            }
+            auto& l = tl[regular[owner(i, h, j)]];
             l.push_back({(short)i, (short)j, (unsigned char)h, (unsigned char)nupd, (unsigned char)has_trsm, (unsigned char)has_m,
-                         (short)(o.first.first < 0 ? 0 : o.first.first), 0});
+                         (short)dl, 0, 0});
             if (l.size() > most) most = l.size();
         }
         if (most <= 32) {
@@ -1287,6 +1331,7 @@ int build_plan(int T, int G, int NG, int mform, ChainPlan* out) {
             GPB_CUDA(cudaMemcpy(p.tile_off, off.data(), (nv + 1) * sizeof(int), cudaMemcpyHostToDevice));
         }
     }
+    if (band > 0 && !p.tiles) { gpb_set_error("dataflow plan: diagonal band does not fit 32 tiles per group"); return GPB_ERR_ARG; }
     g_plans[{{T, G}, NG + (express ? 100 : 0)}] = p;
     *out = p;
     return GPB_OK;
@@ -1342,7 +1387,11 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     int mform = gpb_get_option("chain_mform");      // 0 -> level 1; 2 = off; 1, 3, 4 = levels (build_plan)
     if (mform == 0) mform = 1;
     if (mform == 2 || !pipelined || lists || gpb_get_option("chain_express") == 1) mform = 0;
-    stt = build_plan(T, G, NG, mform, &plan);
+    // diagonal band on dedicated SMs: chain_band = number of band SMs (0 -> default, 1 = off)
+    int band = gpb_get_option("chain_band");
+    if (band == 0) band = 1;
+    if (band == 1 || mform != 1 || T < 12 || T > 40 || G < num_sms) band = 0;
+    stt = build_plan(T, G, NG, mform, band, &plan);
     if (stt) return stt;
     // flag words: one grow-only set per stream (two factorisations on one stream are serialised anyway)
     // (+ the chain's phase clocks, 8 per step, and the workers' accounting behind the flags)

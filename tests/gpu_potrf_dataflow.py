@@ -8,7 +8,7 @@ import torch
 from gaussian_processes_b200 import _lib, engine, device as D
 from conftest import synth_xy
 
-sizes = [int(a) for a in sys.argv[1:] if not a.startswith(("d", "g", "s", "e", "m", "f", "u", "h", "i"))] or [256, 384, 1024, 2048, 4096, 8192]
+sizes = [int(a) for a in sys.argv[1:] if not a.startswith(("d", "g", "s", "e", "m", "f", "u", "h", "i", "b", "x"))] or [256, 384, 1024, 2048, 4096, 8192]
 for a in sys.argv[1:]:
     if a.startswith("d"):
         _lib.set_option("chain_diag", int(a[1:]))
@@ -22,6 +22,10 @@ for a in sys.argv[1:]:
         _lib.set_option("chain_fuse", int(a[1:]))
     if a.startswith("u"):
         _lib.set_option("chain_fuse_guard", int(a[1:]))
+    if a.startswith("b"):
+        _lib.set_option("chain_band", int(a[1:]))
+    if a.startswith("x"):
+        _lib.set_option("chain_band_x", int(a[1:]))
     if a.startswith("i"):
         _lib.set_option("chain_imminent", int(a[1:]))
     if a.startswith("h"):

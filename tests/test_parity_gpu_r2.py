@@ -467,3 +467,16 @@ def test_gp_not_positive_definite_above_one_block():
     assert gp.log_lh == -np.inf and gp.lh == 0 and np.isnan(gp.dloglh_dtheta).all()
     with pytest.raises(np.linalg.LinAlgError):
         gp.Lxx
+
+
+def test_dataflow_potrf_diagonal_band_variant():
+    """The diagonal-band variant (near-diagonal tiles handed over to dedicated SMs; off by default, it needs the
+    whole GPU: N >= 3072) gives the same factor."""
+    import torch
+    n = 3072
+    L0, W0, i0, K = _factor_one(n, {})
+    for opts in ({"chain_band": 12}, {"chain_band": 16, "chain_band_x": 1}):
+        L1, W1, i1, _ = _factor_one(n, dict(opts))
+        assert i0 == 0 and i1 == 0
+        assert float((L1 - L0).abs().max()) <= 1e-12 * float(L0.abs().max()), opts
+        assert float((W1 - W0).abs().max()) <= 1e-11 * float(W0.abs().max()), opts
