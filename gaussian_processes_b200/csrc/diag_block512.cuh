@@ -342,6 +342,11 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                     for (int c = 0; c < SB; c++) St[lane * DLD + c] = a[c];
                     __syncwarp();
                     for (int r = 0; r < SB; r++) Ab[r * SLD + lane] = St[r * DLD + lane];
+                } else if (wid == 1 && bb > 0) {
+                    // previous L column -> global, first half (second half: warp 5 after its inverse).  Both sit on
+                    // sub-partition 1, which has no rows-below warp from S1 on: next to one, the store loop was starved
+                    // (its few instructions are refetched from L2 while 25 KB of straight-line code stream by)
+                    store_Lcol(bb - 1, lane, 64);
                 }
             } else if (wid == 5) {
                 if (bb > 0) {
@@ -431,10 +436,9 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                         __syncwarp();
                         store_Wdiag(bb - 1, lane, 32);
                     }
+                    store_Lcol(bb - 1, 32 + lane, 64);
                     if (dclk && lane == 0) dclk[200 + ph * 6 + 3] = clock64();
                 }
-            } else if (wid == 6 || wid == 7) {
-                if (bb > 0) store_Lcol(bb - 1, tid - 6 * 32, 64);      // previous L column -> global
             } else if (wid >= 9 && (wid & 3) != 0) {
                 // (warps 4, 8, 12 share the sweep's sub-partition and stay idle while it runs)
                 const int slot = wid - 9 - (wid > 12);                  // warps 9 10 11 13 14 15 -> 0..5
@@ -462,14 +466,14 @@ __device__ __forceinline__ void diag_block_body512(double* A, long long ld, doub
                     pair_sync = true;
                 }
             }
-            if (lpub && bb == 4 && wid >= 5 && wid <= 7) {
+            if (lpub && bb == 4 && (wid == 1 || wid == 5)) {
                 // last block column of L (warps 6, 7) and its inverted diagonal block (warp 5) are stored: publish.
                 // (ONE barrier instruction for the three warps: synccheck rejects a named barrier whose
                 //  participants arrive from different instructions.)  Columns 0..2 are released by warp 15 at the
                 // start of the NEXT phase instead: the release fence waits 2-5 k cycles for the stores to be
                 // acknowledged, and inside the sweep phase that made warp 5 the last warp at every phase barrier.
                 __syncwarp();
-                asm volatile("bar.sync 6, 96;\n" ::: "memory");
+                asm volatile("bar.sync 6, 64;\n" ::: "memory");
                 if (dclk && wid == 5 && lane == 0) dclk[200 + ph * 6 + 4] = clock64();
                 if (wid == 5 && lane == 0) {
                     __threadfence();
