@@ -90,6 +90,7 @@ static GpbOption g_options[] = {
     {"chain_imminent", "GPB_CHAIN_IMMINENT", 0, false},     // ... "imminent": due within this many steps (default 1)
     {"chain_band", "GPB_CHAIN_BAND", 0, false},             // SMs dedicated to the tiles next to the diagonal (1 = off)
     {"chain_band_x", "GPB_CHAIN_BAND_X", 0, false},         // L-form steps of a band tile taken over by its band group (default 2)
+    {"lauum_fuse", "GPB_LAUUM_FUSE", 0, false},             // 1 = gradient brackets in the epilogue of the lauum GEMM (K^-1 not stored in the batched evaluator); measured slower, default off
     {"chain_sched", "GPB_CHAIN_SCHED", 0, false},           // workers: 0 = most urgent runnable half tile first, 1 = in-order task lists
     {"chain_group", "GPB_CHAIN_GROUP", 0, false},           // 0 = pipelined chain group (sweeping CTA + 8 helpers + inverter), 8 or 4 = the first chain group of that many CTAs
 };
@@ -584,12 +585,22 @@ static int eval_group(int kind, const double* thetas, int batch, const double* x
         if (want_grad) {
             stt = gpb_launch_trtri(w.L, np_, np_, mstride, batch, w.W, np_, mstride, w.V, np_, mstride, w.Ki, np_, mstride, st);
             if (stt) return stt;
-            stt = gpb_launch_lauum(w.V, np_, np_, mstride, batch, w.Ki, np_, mstride, st);
-            if (stt) return stt;
-            const int jsl[3] = {1, 2, 3};
-            stt = gpb_launch_grad_reduce(kind, nullptr, w.Pb, batch, x, n, w.Ki, np_, mstride, w.alpha, np_,
-                                         gpb_n_kparams(kind), jsl, w.partial, w.out8, st);
-            if (stt) return stt;
+            if (gpb_lauum_grad_available()) {
+                // K^-1 = V V^T never reaches memory: the gradient brackets are taken from its tiles in the GEMM's
+                // epilogue (nothing else reads K^-1 in the batched evaluator)
+                GpbLauumFuse f;
+                f.kind = kind; f.store = 0; f.n = n; memset(&f.P, 0, sizeof(KParams)); f.Pb = w.Pb; f.x = x;
+                f.alpha = w.alpha; f.astride = np_; f.partial = w.partial;
+                stt = gpb_launch_lauum_grad(w.V, np_, np_, mstride, batch, w.Ki, np_, mstride, f, w.out8, st);
+                if (stt) return stt;
+            } else {
+                stt = gpb_launch_lauum(w.V, np_, np_, mstride, batch, w.Ki, np_, mstride, st);
+                if (stt) return stt;
+                const int jsl[3] = {1, 2, 3};
+                stt = gpb_launch_grad_reduce(kind, nullptr, w.Pb, batch, x, n, w.Ki, np_, mstride, w.alpha, np_,
+                                             gpb_n_kparams(kind), jsl, w.partial, w.out8, st);
+                if (stt) return stt;
+            }
         }
     }
     eval_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.out3, w.out8, w.info, w.Pb, kind, want_grad, batch, result);
@@ -744,15 +755,29 @@ int gpb_gp_stages(int kind, const double* theta, const double* x, const double* 
         stt = gpb_launch_trtri(w.L, np_, np_, 0, 1, w.W, np_, 0, w.V, np_, 0, w.Ki, np_, 0, st);
         if (stt) return stt;
     }
-    if (stages & 4u) {          // Ki = V V^T
-        stt = gpb_launch_lauum(w.V, np_, np_, 0, 1, w.Ki, np_, 0, st);
-        if (stt) return stt;
+    bool grad_fused = false;
+    if (stages & 4u) {          // Ki = V V^T  (with the gradient brackets in its epilogue when both are asked for)
+        if ((stages & 8u) && gpb_lauum_grad_available()) {
+            if (side) {             // alpha of the side stream
+                GPB_CUDA(cudaStreamWaitEvent(st, g_join_ev[0], 0));
+                side = false;
+            }
+            GpbLauumFuse f;
+            f.kind = kind; f.store = 1; f.n = n; f.P = P; f.Pb = nullptr; f.x = x;
+            f.alpha = w.alpha; f.astride = np_; f.partial = w.partial;
+            stt = gpb_launch_lauum_grad(w.V, np_, np_, 0, 1, w.Ki, np_, 0, f, w.out8, st);
+            if (stt) return stt;
+            grad_fused = true;
+        } else {
+            stt = gpb_launch_lauum(w.V, np_, np_, 0, 1, w.Ki, np_, 0, st);
+            if (stt) return stt;
+        }
     }
     if (side) {                 // alpha, out3 of the side stream
         GPB_CUDA(cudaStreamWaitEvent(st, g_join_ev[0], 0));
         side = false;
     }
-    if (stages & 8u) {          // a^T dK_i a, sum(Ki o dK_i), tr Ki, a.a
+    if ((stages & 8u) && !grad_fused) {          // a^T dK_i a, sum(Ki o dK_i), tr Ki, a.a
         const int jsl[3] = {1, 2, 3};
         stt = gpb_launch_grad_reduce(kind, &P, nullptr, 1, x, n, w.Ki, np_, 0, w.alpha, np_, nkp, jsl, w.partial,
                                      w.out8, st);

@@ -441,8 +441,6 @@ int gpb_launch_fused_matvec(int kind, const KParams* P, const KParams* Pb, int b
 //    regenerated from x on the fly: one pass over Ki is the only HBM traffic.
 //    Output layout (16 doubles): t0[0..5], t1[0..5], tr(Ki), a.a, 0, 0
 // ---------------------------------------------------------------------------
-#define GPB_RED_MAXS 6
-#define GPB_RED_WIDTH 16
 struct GradArgs {
     KParams P;
     const KParams* Pb;
@@ -607,7 +605,16 @@ int gpb_grad_reduce_blocks(long long n) {
     long long nb = (n + 7) / 8;
     if (nb > 148 * 4) nb = 148 * 4;
     if (nb < 1) nb = 1;
+    // the fused lauum epilogue writes one row per CTA of its lower-triangular 64 x 128 tile grid
+    const long long tn = (n + GPB_NB - 1) / GPB_NB;
+    if (tn * (tn + 1) > nb) nb = tn * (tn + 1);
     return (int)nb;
+}
+
+int gpb_launch_sum_partials(const double* partial, int nblk, int batch, double* out16, cudaStream_t st) {
+    sum_partials_kernel<<<batch, 256, 0, st>>>(partial, nblk, GPB_RED_WIDTH, out16);
+    GPB_LAUNCH_CHECK("sum_partials_kernel");
+    return GPB_OK;
 }
 static int grad_reduce_blocks_used(long long n, bool one_object) {
     // batches: four rows per warp (strided, so the triangular row lengths balance): with one row per warp the
@@ -615,7 +622,11 @@ static int grad_reduce_blocks_used(long long n, bool one_object) {
     // One GP object (parameters by value; the batched evaluator passes a parameter array even for one candidate, so
     // a candidate's sums never depend on how the batch was split): one row per warp -- 128 CTAs left the GPU at 7
     // warps per SM (136 us at N = 4096, 0.5 TB/s).
-    if (one_object) return gpb_grad_reduce_blocks(n);
+    if (one_object) {
+        long long nb1 = (n + 7) / 8;
+        if (nb1 > 148 * 4) nb1 = 148 * 4;
+        return (int)(nb1 < 1 ? 1 : nb1);
+    }
     long long nb = (n + 31) / 32;
     if (nb > 148 * 4) nb = 148 * 4;
     if (nb < 1) nb = 1;

@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "kfunctors.cuh"
 #include "launch.h"
 
 namespace {
@@ -250,9 +251,10 @@ template <int BM> struct TmaCfg {
     static constexpr int MIN_CTAS = (BM == 128) ? 1 : 2;
 };
 
-template <int BM>
-__global__ void __launch_bounds__(TmaCfg<BM>::THREADS, TmaCfg<BM>::MIN_CTAS)
-gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+// FUSE: 0 = plain GEMM; 1 + kernel kind = lauum with the gradient brackets in the epilogue (GpbLauumFuse, launch.h)
+template <int BM, int FUSE>
+__device__ __forceinline__ void gemm_nt_tma_body(const GpbGemm& p, const CUtensorMap& mapA, const CUtensorMap& mapB,
+                                                 const GpbLauumFuse* fp) {
     using Cfg = TmaCfg<BM>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -389,6 +391,71 @@ gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, co
     // mirror is a different matrix
     bool mirror = (Ct != nullptr) && !(p.lower_only && diag_tile && Ct == C);
     if (Ct != nullptr && in_diag && col0_w < row0_w) mirror = true;
+    if constexpr (FUSE > 0) {
+        // ---- gradient brackets of this tile (all 8 consumer warps take part in the reduction; the producer warp is gone)
+        constexpr int KIND = FUSE - 1;
+        constexpr int NP = (KIND == GPB_GAUSSIAN) ? 2 : 3;
+        constexpr unsigned NEED = (KIND == GPB_GAUSSIAN) ? 0x6u : 0xEu;
+        const GpbLauumFuse& f = *fp;
+        __shared__ KParams sP;
+        __shared__ double sred[8][2 * NP + 2];
+        if (f.Pb) {
+            const double* src = reinterpret_cast<const double*>(f.Pb + bz);
+            double* dstp = reinterpret_cast<double*>(&sP);
+            for (int i = tid; i < (int)(sizeof(KParams) / 8); i += Cfg::CONSUMERS) dstp[i] = src[i];
+        } else if (tid == 0) {
+            sP = f.P;
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::CONSUMERS) : "memory");
+        const double* al = f.alpha + bz * f.astride;
+        double v[2 * NP + 2];
+#pragma unroll
+        for (int q = 0; q < 2 * NP + 2; q++) v[q] = 0.0;
+        if (!skip_mma) {
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) {
+                const int r = m0 + wm * 32 + mi * 8 + g;
+                if (r >= f.n) continue;
+                const double xr = f.x[r], ar = al[r];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int c = n0 + wn * 32 + ni * 8 + 2 * t + e;
+                        if (c > r) continue;
+                        // strict lower part counts twice (symmetry), the diagonal once
+                        const double wgt = (c < r) ? 2.0 : 1.0;
+                        const double k = p.alpha * acc[mi][ni][e] * wgt;
+                        const double aw = ar * al[c] * wgt;
+                        double u[10];
+                        gpb_eval_unique<KIND>(sP, xr - f.x[c], NEED, u);
+#pragma unroll
+                        for (int q = 0; q < NP; q++) { v[q] += u[1 + q] * aw; v[NP + q] += u[1 + q] * k; }
+                        if (c == r) { v[2 * NP] += k; v[2 * NP + 1] += ar * ar; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2 * NP + 2; q++) {
+            const double sq = warp_sum(v[q]);
+            if (lane == 0) sred[wid][q] = sq;
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::CONSUMERS) : "memory");
+        if (tid < GPB_RED_WIDTH) {
+            // partial row: t0[6] | t1[6] | tr | a.a | 0 0
+            int q = -1;
+            if (tid < NP) q = tid;
+            else if (tid >= GPB_RED_MAXS && tid < GPB_RED_MAXS + NP) q = NP + (tid - GPB_RED_MAXS);
+            else if (tid == 12) q = 2 * NP;
+            else if (tid == 13) q = 2 * NP + 1;
+            double sq = 0.0;
+            if (q >= 0)
+                for (int w = 0; w < Cfg::CONSUMERS / 32; w++) sq += sred[w][q];
+            f.partial[((long long)blockIdx.z * gridDim.x + blockIdx.x) * GPB_RED_WIDTH + tid] = sq;
+        }
+        if (!f.store) return;
+    }
     if (skip_mma) return;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
@@ -411,6 +478,21 @@ gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, co
             }
         }
     }
+}
+
+template <int BM>
+__global__ void __launch_bounds__(TmaCfg<BM>::THREADS, TmaCfg<BM>::MIN_CTAS)
+gemm_nt_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+    gemm_nt_tma_body<BM, 0>(p, mapA, mapB, nullptr);
+}
+
+// lauum (Ki = V V^T, 64 x 128 tiles) with the gradient brackets in the epilogue: its own instantiation, so the plain
+// GEMM keeps its 96 registers
+template <int FUSE>
+__global__ void __launch_bounds__(TmaCfg<64>::THREADS, TmaCfg<64>::MIN_CTAS)
+lauum_grad_tma_kernel(const GpbGemm p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                      const __grid_constant__ GpbLauumFuse f) {
+    gemm_nt_tma_body<64, FUSE>(p, mapA, mapB, &f);
 }
 
 }  // namespace
@@ -520,4 +602,55 @@ int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st) {
     if (tma_ok && gpb_get_option("gemm_impl") != 1)
         return bm == 128 ? launch_tma<128>(p, batch, st) : launch_tma<64>(p, batch, st);
     return bm == 128 ? launch_cfg<128>(p, batch, st) : launch_cfg<64>(p, batch, st);
+}
+
+// Measured on B200 (bench.py, same box): fused / separate  headline 452.8 / 461.5 evals/s, C4 19.6 k / 21.1 k evals/s, one GP
+// object 3.39 / 3.33 ms.  The separate grad_jac_kernel overlaps the GEMMs of the other evaluator streams and K^-1 stays in
+// L2 between the two kernels; in the epilogue the same exp work sits on the SMs the DMMA pipe is waiting for (and the 32
+// accumulators spill around it at 96 registers).  So the fused path is OFF unless "lauum_fuse" = 1.
+bool gpb_lauum_grad_available() {
+    int bm = gpb_get_option("gemm_bm");
+    return (bm == 0 || bm == 64) && gpb_get_option("gemm_impl") != 1 && gpb_get_option("lauum_fuse") == 1;
+}
+
+int gpb_launch_lauum_grad(const double* V, long long n, long long ldv, long long sV, int batch, double* Ki,
+                          long long ldk, long long sK, const GpbLauumFuse& f, double* out16, cudaStream_t st) {
+    GPB_REQUIRE(n > 0 && n % GPB_NB == 0, "n must be a positive multiple of 128");
+    GPB_REQUIRE(gpb_lauum_grad_available(), "fused lauum not available with these options");
+    GPB_REQUIRE(f.kind == GPB_GAUSSIAN || f.kind == GPB_PERIODIC, "unknown kernel kind");
+    GPB_REQUIRE(f.x && f.alpha && f.partial && out16 && (Ki || !f.store), "null pointer");
+    GPB_REQUIRE(batch >= 1 && batch <= 65535 && ldv % 2 == 0 && sV % 2 == 0 && n < (1LL << 31) && ldv < (1LL << 31), "bad extents");
+    using Cfg = TmaCfg<64>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPB_CUDA(cudaFuncSetAttribute(lauum_grad_tma_kernel<1 + GPB_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        GPB_CUDA(cudaFuncSetAttribute(lauum_grad_tma_kernel<1 + GPB_PERIODIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int stt = encode_init();
+    if (stt) return stt;
+    GpbGemm g = gpb_gemm_default();
+    g.A = V; g.lda = ldv; g.sA = sV;
+    g.B = V; g.ldb = ldv; g.sB = sV;
+    g.C = Ki; g.ldc = ldk; g.sC = sK;
+    g.Ct = Ki; g.ldct = ldk; g.sCt = sK;
+    g.M = g.N = g.K = (int)n;
+    g.a_tri = 2; g.b_tri = 2; g.lower_only = 1;
+    const long long off = (long long)(batch - 1) * sV;
+    GPB_REQUIRE((off % ldv) + n <= ldv && off / ldv + n < (1LL << 31), "batch stride does not map onto one tensor map");
+    CUtensorMap mapA, mapB;
+    stt = make_map(&mapA, V, ldv, off / ldv + n, 64);
+    if (stt) return stt;
+    stt = make_map(&mapB, V, ldv, off / ldv + n, BN);
+    if (stt) return stt;
+    const int tn = (int)(n / BN);
+    const int nblk = tn * (tn + 1) / 2 * 2;
+    dim3 grid((unsigned)nblk, 1, (unsigned)batch);
+    {
+        GpbProfScope prof(GPB_KC_GEMM, st);
+        if (f.kind == GPB_GAUSSIAN) lauum_grad_tma_kernel<1 + GPB_GAUSSIAN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, mapA, mapB, f);
+        else lauum_grad_tma_kernel<1 + GPB_PERIODIC><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, mapA, mapB, f);
+        GPB_LAUNCH_CHECK("lauum_grad_tma_kernel");
+    }
+    return gpb_launch_sum_partials(f.partial, nblk, batch, out16, st);
 }

@@ -35,6 +35,30 @@ inline GpbGemm gpb_gemm_default() {
 
 int gpb_launch_gemm(const GpbGemm& p, int batch, cudaStream_t st);
 
+#define GPB_RED_MAXS 6      // slices per reduction pass
+#define GPB_RED_WIDTH 16    // doubles per partial row: t0[6] | t1[6] | tr | a.a | 0 0
+
+// Gradient brackets in the epilogue of the lauum GEMM (Ki = V V^T, lower tiles): while a tile of K^-1 is in registers
+// the kernel-derivative tiles are regenerated from x and  t0[q] += a_r a_c dK_q(r,c),  t1[q] += Ki_rc dK_q(r,c),
+// tr += Ki_rr,  aa += a_r^2  are accumulated (gp/ext/gp_c.pyx:41-49); one row of 16 partials per CTA.
+struct GpbLauumFuse {
+    int kind;                // GPB_GAUSSIAN | GPB_PERIODIC
+    int store;               // 0: K^-1 itself is not needed, its tiles are not written
+    long long n;             // valid extent (identity pad excluded)
+    KParams P;               // parameters by value (one object) ...
+    const KParams* Pb;       // ... or one entry per batch member
+    const double* x;
+    const double* alpha;
+    long long astride;
+    double* partial;         // [batch][CTAs per matrix][16]
+};
+// Ki = V V^T with the fused gradient reduction; out16[b] = {t0[6] | t1[6] | tr | a.a | 0 0}.  Returns GPB_ERR_ARG
+// (nothing launched) when the fused path is not available (gemm_bm / gemm_impl options): use lauum + grad_reduce.
+bool gpb_lauum_grad_available();
+int gpb_launch_lauum_grad(const double* V, long long n, long long ldv, long long sV, int batch, double* Ki,
+                          long long ldk, long long sK, const GpbLauumFuse& f, double* out16, cudaStream_t st);
+int gpb_launch_sum_partials(const double* partial, int nblk, int batch, double* out16, cudaStream_t st);
+
 // run-time tuning knobs (api.cu): "eval_streams", "gemm_bm", "potrf_inner"; 0 = default
 int gpb_get_option(const char* name);
 

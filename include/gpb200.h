@@ -277,6 +277,7 @@ int64_t gpb_launch_count(void);
  *   "chain_horizon" (GPB_CHAIN_HORIZON) updates of tiles not needed for this many steps yield while their group has a tile
  *                                     due within "chain_imminent" steps (defaults 3 and 1; 100 = off)
  *   "chain_fuse_guard", "chain_express"  scheduling experiments (csrc/chain.cu)
+ *   "lauum_fuse"   (GPB_LAUUM_FUSE)   1 = gradient brackets in the epilogue of the K^-1 = V V^T GEMM (measured slower: off)
  *   "stage_overlap" (GPB_STAGE_OVERLAP) 2 = gpb_gp_stages keeps the triangular solves on the caller's stream
  * None of them changes a result beyond rounding; the dataflow variants are compared in tests/test_parity_gpu_r2.py. */
 int gpb_set_option(const char* name, int value);

@@ -480,3 +480,31 @@ def test_dataflow_potrf_diagonal_band_variant():
         assert i0 == 0 and i1 == 0
         assert float((L1 - L0).abs().max()) <= 1e-12 * float(L0.abs().max()), opts
         assert float((W1 - W0).abs().max()) <= 1e-11 * float(W0.abs().max()), opts
+
+
+@pytest.mark.parametrize("kparams", [(1.0, 0.5), (0.9, 0.8, 1.4)])
+def test_gradient_brackets_in_the_lauum_epilogue(oracle, kparams):
+    """Option lauum_fuse = 1 (gradient brackets accumulated from the tiles of K^-1 inside the GEMM epilogue; in the
+    batched evaluator K^-1 is then never stored) against the default path and the oracle: one object and a batch,
+    both kernels, a size with an identity pad."""
+    from gaussian_processes_b200 import _lib
+    n = 700
+    x, y = synth_xy(n, 4)
+    K = GaussianKernel(*kparams) if len(kparams) == 2 else PeriodicKernel(*kparams)
+    th = np.array([list(kparams) + [0.8], [v * 1.1 for v in kparams] + [1.2], [v * 0.9 for v in kparams] + [0.6]])
+    gp = GP(K, x, y, s=0.8)
+    base = (gp.log_lh, gp.dloglh_dtheta.copy(), gp.batch_eval(th))
+    _lib.set_option("lauum_fuse", 1)
+    try:
+        gp2 = GP(K.copy(), x, y, s=0.8)
+        fused = (gp2.log_lh, gp2.dloglh_dtheta.copy(), gp2.batch_eval(th))
+        Ki = gp2.inv_Kxx                     # the one-object path still stores K^-1
+    finally:
+        _lib.set_option("lauum_fuse", 0)
+    assert fused[0] == base[0]
+    assert_parity(fused[1], base[1], 1e-11, "fused gradient, one object")
+    assert_parity(fused[2][0], base[2][0], 1e-13, "fused batch log_lh")
+    assert_parity(fused[2][1], base[2][1], 1e-11, "fused batch gradient")
+    o = oracle.OracleGP(oracle.GAUSSIAN if len(kparams) == 2 else oracle.PERIODIC, kparams, x, y, 0.8)
+    assert_parity(fused[1], o.dloglh_dtheta, RTOL, "fused gradient vs oracle")
+    assert_parity(Ki, o.inv_Kxx, 1e-8, "K^-1 stored by the fused launch")
