@@ -81,7 +81,9 @@ int gpb_post_var(int kind, const double* theta, const double* Z, int64_t ldz, in
  * sub-blocks is zeroed, everything else above the diagonal is left untouched -- see
  * gpb_tril for the dense lower-triangular matrix scipy returns.  Also
  * writes the inverted 128x128 diagonal blocks into W (lower) and, if V != NULL, their
- * transposes into V.  info[b] = 0 or first failing column + 1.
+ * transposes into V.  The tiles of W strictly below its diagonal blocks are WORKSPACE of the call
+ * (a single matrix factored by the dataflow launch keeps L tiles there until it copies them home);
+ * gpb_trtri overwrites every one of them.  info[b] = 0 or first failing column + 1.
  * Replaces scipy.linalg.cholesky(lower=True) at gp/gp.py:294.                       */
 int gpb_potrf(double* A, int64_t n, int64_t ld, int64_t stride_a, int batch, double* W,
               int64_t ldw, int64_t stride_w, double* V, int64_t ldv, int64_t stride_v,
