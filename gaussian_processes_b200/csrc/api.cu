@@ -83,7 +83,7 @@ static GpbOption g_options[] = {
     {"chain_diag", "GPB_CHAIN_DIAG", 0, false},             // 2 = the chain CTA factors diagonal blocks with the 256-thread body
     {"chain_express", "GPB_CHAIN_EXPRESS", 0, false},       // 1 = six express worker groups for the chain-adjacent tiles (measured: no gain)
     {"chain_mform", "GPB_CHAIN_MFORM", 0, false},           // M form of the workers' last update(s) of a tile: 0/1 = step j-1, 3, 4 = more (chain.cu build_plan), 2 = off
-    {"chain_fuse", "GPB_CHAIN_FUSE", 0, false},             // most backlog steps of a half tile applied by one worker task (default 4)
+    {"chain_fuse", "GPB_CHAIN_FUSE", 0, false},             // most backlog steps of a half tile applied by one worker task (default 8)
     {"chain_fuse_guard", "GPB_CHAIN_FUSE_GUARD", 0, false}, // no fused task while a more urgent tile of the group is due within this many steps (default 2, 100 = off)
     {"stage_overlap", "GPB_STAGE_OVERLAP", 0, false},       // 2 = gpb_gp_stages keeps the triangular solves on the caller's stream
     {"chain_horizon", "GPB_CHAIN_HORIZON", 0, false},       // far tiles (deadline > step + horizon) yield while their group has an imminent tile (default 3, 100 = off)

@@ -1429,7 +1429,10 @@ int gpb_launch_potrf_dataflow(double* A, long long n, long long ld, double* W, l
     a.fuse_guard = gpb_get_option("chain_fuse_guard");
     if (a.fuse_guard <= 0) a.fuse_guard = 2;
     if (a.fuse_guard >= 100) a.fuse_guard = -1000;       // (off)
-    if (a.fuse <= 0) a.fuse = 4;             // measured 1 / 2 / 3 / 4 / 8 at N = 4096: 1.68 / 1.65 / 1.60 / 1.59 / 1.59 ms, N = 6144: 4.15 / 3.83 / 3.72 / 3.69 / 3.79
+    // measured before the yield policy: 1 / 2 / 3 / 4 / 8 at N = 4096: 1.68 / 1.65 / 1.60 / 1.59 / 1.59 ms, N = 6144: 4.15 / 3.83 / 3.72 /
+    // 3.69 / 3.79; with it (far tiles no longer start right before urgent ones): 4 / 8 / 12 at N = 6144: 3.54 / 3.49 / 3.48,
+    // N = 8192: 7.46 / 7.29 / 7.29
+    if (a.fuse <= 0) a.fuse = 8;
     a.NG = NG;
     a.pipelined = pipelined;
     a.diag512 = gpb_get_option("chain_diag");           // 0/1 default body, 2 the 256-thread body, 3.. experiments

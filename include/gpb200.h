@@ -275,7 +275,7 @@ int64_t gpb_launch_count(void);
  *   "chain_diag"   (GPB_CHAIN_DIAG)   2 = the chain CTA factors diagonal blocks with the 256-thread body
  *   "chain_sched"  (GPB_CHAIN_SCHED)  workers: 0 = most urgent runnable half tile first, 1 = in-order task lists
  *   "chain_mform"  (GPB_CHAIN_MFORM)  M form of a tile's last worker update(s): 0/1 = last step, 3 / 4 = more, 2 = off
- *   "chain_fuse"   (GPB_CHAIN_FUSE)   most backlog steps of a half tile applied by one worker task (default 4)
+ *   "chain_fuse"   (GPB_CHAIN_FUSE)   most backlog steps of a half tile applied by one worker task (default 8)
  *   "chain_horizon" (GPB_CHAIN_HORIZON) updates of tiles not needed for this many steps yield while their group has a tile
  *                                     due within "chain_imminent" steps (defaults 3 and 1; 100 = off)
  *   "chain_fuse_guard", "chain_express"  scheduling experiments (csrc/chain.cu)
